@@ -1,0 +1,128 @@
+/* mprb -- C ABI of the B200 tile-recursive implicit-surface renderer.
+ *
+ * This is the drop-in boundary for the one hot path of mkeeter/mpr:
+ * mpr::Context::render2D / render3D and the kernels beneath them.  The
+ * reference has no FFI for this path -- its boundary is the C++ struct surface
+ * of inc/tape.hpp, inc/context.hpp and inc/util.hpp -- so each entry point
+ * below names the reference member it stands behind.  The C++ headers in
+ * mpr_b200/inc/ re-create those structs on top of this ABI (see
+ * INTEGRATION.md); plain pointers and sizes only, no C++ or torch types.
+ *
+ * Conventions: every function returning int yields 0 on success and a
+ * non-zero MPRB_E_* code otherwise; mprb_last_error() describes the most
+ * recent failure on the calling thread.  Matrices are column-major floats,
+ * the layout Eigen::Matrix3f / Matrix4f use in the reference.  All buffers
+ * handed out by mprb_ctx_buffers() are CUDA managed memory: dereferenceable on
+ * the host after a render call returns (calls return only after the device
+ * has finished, like the reference's cudaDeviceSynchronize at
+ * src/context.cu:1279 / :1457) and on the device that owns the context.
+ */
+#ifndef MPRB_H
+#define MPRB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPRB_OK 0
+#define MPRB_E_CUDA 1        /* a CUDA runtime call failed */
+#define MPRB_E_ARG 2         /* invalid argument */
+#define MPRB_E_OVERFLOW 3    /* a tile list outgrew its (worst-case-capped) array */
+#define MPRB_E_PARSE 4       /* malformed .frep input */
+
+typedef struct mprb_ctx mprb_ctx;
+typedef struct mprb_tape mprb_tape;
+
+/* Same layout as mpr::TileNode (reference inc/context.hpp:23-27). */
+typedef struct mprb_tile_node {
+    int32_t position; /* linear tile index at its level, or -1 once resolved */
+    int32_t tape;     /* index of this tile's tape header in tape_data */
+    int32_t next;     /* rank among active tiles (children at next*64+i), or -1 */
+} mprb_tile_node;
+
+/* Mirrors the data members of mpr::Context (reference inc/context.hpp:60-72). */
+typedef struct mprb_buffers {
+    int32_t image_size_px;
+    int32_t* filled[4];           /* stages[i].filled; [3] is the final image / heightmap */
+    mprb_tile_node* tiles[4];     /* stages[i].tiles */
+    uint64_t tile_array_size[4];  /* stages[i].tile_array_size: entries valid after the last frame */
+    uint64_t* tape_data;          /* subtape arena; the root tape is at cell 0 */
+    int32_t* tape_index;          /* cells of the arena in use after the last frame */
+    int32_t* num_active_tiles;    /* survivors of the last interval level */
+    uint32_t* normals;            /* 0xFFzzyyxx per pixel (3D only) */
+} mprb_buffers;
+
+typedef struct mprb_ctx_opts {
+    int32_t device;        /* CUDA device ordinal; -1 = current device */
+    int64_t num_subtapes;  /* arena size in 64-cell chunks; 0 = 640000
+                              (reference inc/parameters.hpp:18-22; 6400000 with BIG_SERVER) */
+    /* Multi-GPU sharding: this context renders only the level-0 tile rows
+     * [row_begin, row_end) (64-pixel rows in y); row_end = 0 means "all". */
+    int32_t row_begin;
+    int32_t row_end;
+} mprb_ctx_opts;
+
+/* Per-frame counters, filled by the render calls (device-side; no extra syncs). */
+typedef struct mprb_frame_stats {
+    int32_t n_active[3];      /* ambiguous tiles left after interval level 0, 1, 2 */
+    int32_t tape_index;       /* arena cells in use */
+    int32_t overflow;         /* bit i: stage i+1 tile array was too small */
+    uint64_t i_tiles[3];      /* interval tiles whose tape was walked, per level */
+    uint64_t i_cells[3];      /* tape cells visited by those walks */
+    uint64_t p_tiles[3];      /* tiles that wrote a shortened tape */
+    uint64_t p_cells[3];      /* tape cells visited by the backward walks */
+    uint64_t p_kept[3];       /* arena cells written by pushes */
+    uint64_t f_tiles;         /* float-stage tiles (64 samples each) */
+    uint64_t f_cells;         /* tape cells visited by the float stage */
+    uint64_t n_pixels;        /* normal-pass pixels */
+    uint64_t n_cells;         /* tape cells visited by the normal pass */
+    float gpu_ms;             /* device time of the whole frame (CUDA events) */
+    float kernel_ms[12];      /* device time per launch (only when timing is enabled) */
+    int32_t n_launches;       /* kernels launched for the frame */
+} mprb_frame_stats;
+
+/* ---- context: mpr::Context::Context(int32_t) (src/context.cpp:16-49) ------------ */
+int mprb_ctx_create(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx** out);
+void mprb_ctx_destroy(mprb_ctx* ctx);
+int mprb_ctx_buffers(mprb_ctx* ctx, mprb_buffers* out);
+/* Enables per-kernel CUDA-event timing (fills kernel_ms); off by default. */
+int mprb_ctx_set_timing(mprb_ctx* ctx, int enabled);
+
+/* ---- tape: mpr::Tape (inc/tape.hpp:24-30, upload at src/tape.cpp:223-227) -------- */
+int mprb_tape_create(const uint64_t* host_cells, int32_t n_cells, mprb_tape** out);
+void mprb_tape_destroy(mprb_tape* tape);
+const uint64_t* mprb_tape_data(const mprb_tape* tape);  /* managed memory (Tape::data) */
+int32_t mprb_tape_length(const mprb_tape* tape);        /* Tape::length */
+int32_t mprb_tape_num_slots(const mprb_tape* tape);
+
+/* ---- frames: mpr::Context::render2D / render3D (src/context.cu:1136, :1282) ------ */
+int mprb_render2d(mprb_ctx* ctx, const mprb_tape* tape, const float mat3_colmajor[9], float z);
+int mprb_render3d(mprb_ctx* ctx, const mprb_tape* tape, const float mat4_colmajor[16]);
+
+/* Host-buffer variants: the tape cells come from (pinned or pageable) host
+ * memory and the results are copied into host buffers before returning.
+ * image_out: size*size int32; normals_out: size*size uint32 (may be NULL). */
+int mprb_render2d_host(mprb_ctx* ctx, const uint64_t* host_cells, int32_t n_cells,
+                       const float mat3_colmajor[9], float z, int32_t* image_out);
+int mprb_render3d_host(mprb_ctx* ctx, const uint64_t* host_cells, int32_t n_cells,
+                       const float mat4_colmajor[16], int32_t* depth_out, uint32_t* normals_out);
+
+int mprb_frame_stats_get(mprb_ctx* ctx, mprb_frame_stats* out);
+
+/* ---- host helpers ----------------------------------------------------------------- */
+/* .frep bytes -> packed tape (libfive archive reader + the packer that restates
+ * src/tape.cpp).  *cells_out is malloc'd; release with mprb_free(). */
+int mprb_tape_from_frep(const uint8_t* bytes, size_t n_bytes, int simplify,
+                        uint64_t** cells_out, int32_t* n_cells_out, int32_t* n_slots_out);
+void mprb_free(void* p);
+
+const char* mprb_last_error(void);
+const char* mprb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPRB_H */

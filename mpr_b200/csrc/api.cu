@@ -1,0 +1,608 @@
+// C-ABI entry points of libmprb: context and tape management, and the
+// per-frame launch sequence (see include/mprb.h for the contract).
+//
+// Reference counterparts: Context::Context (src/context.cpp:16-49),
+// Context::render2D (src/context.cu:1136-1280), Context::render3D
+// (src/context.cu:1282-1458), Tape upload (src/tape.cpp:223-227).
+//
+// Unlike the reference, a frame never returns to the host between levels: tile
+// counts live in a device control block (FrameCtl), every tape-walking kernel
+// is a persistent grid pulling work items from a device queue, and tile arrays
+// are sized for the worst case up front.  The only host<->device traffic of a
+// frame is the kernel launches, one 304-byte control-block read-back at the
+// end, and (host-buffer variants only) the tape upload and the image download.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/mprb.h"
+#include "common.cuh"
+#include "host/mprb_host.hpp"
+#include "kernels.cuh"
+#include "libfive/tree/archive.hpp"
+
+using namespace mprb;
+
+static_assert(sizeof(mprb_tile_node) == sizeof(TileNode), "TileNode layout");
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define MPRB_CUDA(expr)                                                              \
+    do {                                                                             \
+        cudaError_t e_ = (expr);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            return fail(MPRB_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                         \
+        }                                                                            \
+    } while (0)
+
+constexpr long long kMaxStageTiles = 64ll << 20;   // cap on any one tile array
+constexpr int kMaxLaunches = 12;
+
+template <typename T>
+cudaError_t managed_alloc(T** out, size_t count, int device) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocManaged(&p, sizeof(T) * std::max<size_t>(count, 1));
+    if (e != cudaSuccess) return e;
+    // Keep pages on the GPU; host reads after a frame migrate on demand.
+    cudaMemAdvise(p, sizeof(T) * std::max<size_t>(count, 1), cudaMemAdviseSetPreferredLocation, device);
+    *out = static_cast<T*>(p);
+    return cudaSuccess;
+}
+
+}  // namespace
+
+struct mprb_tape {
+    uint64_t* cells = nullptr;   // managed
+    int32_t length = 0;
+    int32_t n_slots = 0;
+};
+
+struct mprb_ctx {
+    int device = 0;
+    int size = 0;
+    int sm_count = 0;
+    int row_begin = 0, row_end = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_k[kMaxLaunches + 1] = {};
+    bool timing = false;
+
+    // API-visible (managed) buffers
+    int32_t* filled[4] = {};
+    TileNode* tiles[4] = {};
+    long long tiles_cap[4] = {};
+    uint64_t tile_array_size[4] = {};
+    uint64_t* arena = nullptr;
+    long long arena_cells = 0;
+    int32_t* tape_index = nullptr;
+    int32_t* num_active_tiles = nullptr;
+    uint32_t* normals = nullptr;
+
+    // internal
+    int32_t* active_list[3] = {};
+    FrameCtl* ctl = nullptr;
+    FrameCtl* ctl_host = nullptr;    // pinned
+    uint64_t* stage_cells = nullptr; // pinned staging for host tapes
+    int32_t stage_cells_cap = 0;
+    bool have_3d = false;
+
+    mprb_frame_stats stats = {};
+    std::map<long long, int> occ_cache;
+};
+
+namespace {
+
+int tape_num_slots(const uint64_t* cells, int32_t n) {
+    int mx = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        const uint32_t w = uint32_t(cells[i]);
+        const uint32_t op = w & 0xff;
+        if (op == OP_JUMP) continue;
+        mx = std::max<int>(mx, (w >> 8) & 0xff);
+        mx = std::max<int>(mx, (w >> 16) & 0xff);
+        mx = std::max<int>(mx, w >> 24);
+    }
+    return mx + 1;
+}
+
+int validate_tape(const uint64_t* cells, int32_t n) {
+    if (!cells || n < 2) return fail(MPRB_E_ARG, "tape needs at least a header and an end cell");
+    if ((cells[0] & 0xff) != 0 || (cells[n - 1] & 0xff) != 0)
+        return fail(MPRB_E_ARG, "tape must start with a header cell and finish with an end cell");
+    for (int32_t i = 1; i + 1 < n; ++i) {
+        const uint32_t op = uint32_t(cells[i]) & 0xff;
+        if (op < OP_SQUARE || op > OP_COPY_RHS)
+            return fail(MPRB_E_ARG, "tape cell %d has opcode %u, which is not a clause", i, op);
+    }
+    if (tape_num_slots(cells, n) > 128)
+        return fail(MPRB_E_ARG, "tape uses more than 128 slots (the reference kernels hold 128)");
+    return MPRB_OK;
+}
+
+int ensure_stage(mprb_ctx* c, int stage, long long cap) {
+    if (c->tiles_cap[stage] >= cap) return MPRB_OK;
+    if (c->tiles[stage]) cudaFree(c->tiles[stage]);
+    c->tiles[stage] = nullptr;
+    MPRB_CUDA(managed_alloc(&c->tiles[stage], size_t(cap), c->device));
+    c->tiles_cap[stage] = cap;
+    if (stage < 3) {
+        if (c->active_list[stage]) cudaFree(c->active_list[stage]);
+        c->active_list[stage] = nullptr;
+        MPRB_CUDA(cudaMalloc(&c->active_list[stage], sizeof(int32_t) * size_t(cap)));
+    }
+    return MPRB_OK;
+}
+
+int cached_occupancy(mprb_ctx* c, int kind, int dim, bool root, int n_slots) {
+    const long long key = (long long)kind << 40 | (long long)dim << 32 | (long long)root << 24 | n_slots;
+    auto itr = c->occ_cache.find(key);
+    if (itr != c->occ_cache.end()) return itr->second;
+    int n = 0;
+    if (kind == 0) n = occupancy_eval_tiles(dim, root, n_slots);
+    else if (kind == 1) n = occupancy_eval_voxels(dim, n_slots);
+    else n = occupancy_normals(n_slots);
+    n = std::max(n, 1);
+    c->occ_cache[key] = n;
+    return n;
+}
+
+struct Timer {
+    mprb_ctx* c;
+    int n = 0;
+    void mark() {
+        if (c->timing && n <= kMaxLaunches) cudaEventRecord(c->ev_k[n], c->stream);
+        ++n;
+    }
+};
+
+// The frame proper.  `cells` may be a device/managed pointer (async D2D copy)
+// or a host pointer (async H2D copy through pinned staging).
+int render(mprb_ctx* c, int dim, const uint64_t* cells, int32_t n_cells, bool cells_on_host,
+           int n_slots, const float* matrix, float z)
+{
+    if (!c) return fail(MPRB_E_ARG, "null context");
+    const int S = c->size;
+    cudaStream_t s = c->stream;
+    MPRB_CUDA(cudaSetDevice(c->device));
+    if (n_cells >= c->arena_cells) return fail(MPRB_E_ARG, "tape longer than the arena");
+
+    const int tps0 = S / 64;
+    const long long count0 = dim == 3 ? (long long)tps0 * tps0 * tps0 : (long long)tps0 * tps0;
+    // Stage layout.  3D: 64^3 -> 16^3 -> 4^3 -> voxels (stages 0,1,2,3).
+    // 2D: 64^2 -> 8^2 -> pixels (stages 0,2,3), as in the reference.
+    const int n_levels = dim == 3 ? 3 : 2;
+    int stage_of[3] = {0, dim == 3 ? 1 : 2, 2};
+    int px_of[3] = {64, dim == 3 ? 16 : 8, 4};
+    {
+        long long cap = count0;
+        for (int l = 1; l < n_levels; ++l) {
+            cap = std::min(cap * 64, kMaxStageTiles);
+            if (int e = ensure_stage(c, stage_of[l], cap)) return e;
+        }
+        if (int e = ensure_stage(c, 3, cap)) return e;   // compact survivor list
+    }
+
+    Mat4 m4;
+    Mat3 m3;
+    if (dim == 3) memcpy(m4.d, matrix, sizeof(m4.d));
+    else memcpy(m3.d, matrix, sizeof(m3.d));
+    const void* mat = dim == 3 ? static_cast<const void*>(&m4) : static_cast<const void*>(&m3);
+
+    cudaEventRecord(c->ev_begin, s);
+    Timer tm{c};
+    tm.mark();
+
+    // Root tape to cell 0 of the arena (context.cu:1139-1142); pushed tapes start
+    // at the next 64-cell boundary so every chunk is 512-byte aligned.
+    const int32_t first_free = (n_cells + kChunk - 1) / kChunk * kChunk;
+    launch_begin_frame(c->ctl, first_free, s);
+    if (cells_on_host) {
+        if (c->stage_cells_cap < n_cells) {
+            if (c->stage_cells) cudaFreeHost(c->stage_cells);
+            c->stage_cells = nullptr;
+            MPRB_CUDA(cudaMallocHost(&c->stage_cells, sizeof(uint64_t) * size_t(n_cells)));
+            c->stage_cells_cap = n_cells;
+        }
+        memcpy(c->stage_cells, cells, sizeof(uint64_t) * size_t(n_cells));
+        MPRB_CUDA(cudaMemcpyAsync(c->arena, c->stage_cells, sizeof(uint64_t) * size_t(n_cells),
+                                  cudaMemcpyHostToDevice, s));
+    } else {
+        MPRB_CUDA(cudaMemcpyAsync(c->arena, cells, sizeof(uint64_t) * size_t(n_cells),
+                                  cudaMemcpyDeviceToDevice, s));
+    }
+    MPRB_CUDA(cudaMemsetAsync(c->filled[0], 0, sizeof(int32_t) * size_t(tps0) * tps0, s));
+    if (dim == 3) MPRB_CUDA(cudaMemsetAsync(c->normals, 0, sizeof(uint32_t) * size_t(S) * S, s));
+
+    int q = 0;
+    const int small_grid = c->sm_count * 4;
+    for (int l = 0; l < n_levels; ++l) {
+        const int st = stage_of[l];
+        const bool root = (l == 0);
+        const bool last = (l == n_levels - 1);
+        const int tps = S / px_of[l];
+
+        EvalTilesArgs ea = {};
+        ea.arena = c->arena;
+        ea.tape_index = &c->ctl->tape_cursor;
+        ea.arena_cap = int32_t(c->arena_cells);
+        ea.image = c->filled[st];
+        ea.tiles = c->tiles[st];
+        ea.tiles_cap = int32_t(std::min<long long>(c->tiles_cap[st], INT32_MAX));
+        ea.tps = uint32_t(tps);
+        if (!root) {
+            ea.ptiles = c->tiles[stage_of[l - 1]];
+            ea.pactive = c->active_list[stage_of[l - 1]];
+            ea.n_parents = &c->ctl->n_active[l - 1];
+            ea.ptps = uint32_t(S / px_of[l - 1]);
+        }
+        ea.count0 = int32_t(count0);
+        ea.row_begin = c->row_begin;
+        ea.row_end = c->row_end;
+        ea.ctl = c->ctl;
+        ea.queue = &c->ctl->queue[q++];
+        ea.level = l;
+        ea.n_slots = n_slots;
+        ea.z = z;
+        int grid = c->sm_count * cached_occupancy(c, 0, dim, root, n_slots);
+        if (root) {
+            const long long items = (count0 + 31) / 32;
+            grid = int(std::min<long long>(grid, (items + kEvalWarps - 1) / kEvalWarps));
+        }
+        launch_eval_tiles(dim, root, ea, mat, std::max(grid, 1), s);
+        tm.mark();
+
+        RankArgs ra = {};
+        ra.tiles = c->tiles[st];
+        ra.tiles_cap = ea.tiles_cap;
+        ra.n_parents = root ? nullptr : &c->ctl->n_active[l - 1];
+        ra.count0 = int32_t(count0);
+        ra.tps = tps;
+        ra.image = c->filled[st];
+        ra.n_active = &c->ctl->n_active[l];
+        ra.active_list = c->active_list[st];
+        ra.out_tiles = c->tiles[3];
+        ra.next_cap = last ? c->tiles_cap[3] : c->tiles_cap[stage_of[l + 1]];
+        ra.last_level = last ? 1 : 0;
+        ra.level = l;
+        ra.ctl = c->ctl;
+        int rgrid = small_grid;
+        if (root) rgrid = int(std::min<long long>(small_grid, (count0 + 255) / 256));
+        launch_rank_tiles(dim, ra, std::max(rgrid, 1), s);
+        tm.mark();
+
+        const int next_stage = last ? 3 : stage_of[l + 1];
+        const int next_size = last ? S : S / px_of[l + 1];
+        const long long px = (long long)next_size * next_size;
+        launch_upsample_filled(dim, c->filled[st], c->filled[next_stage], next_size,
+                               int(std::min<long long>(c->sm_count * 8, (px + 255) / 256)), s);
+        tm.mark();
+    }
+
+    {
+        EvalVoxelsArgs va = {};
+        va.arena = c->arena;
+        va.image = c->filled[3];
+        va.tiles = c->tiles[3];
+        va.tiles_cap = int32_t(std::min<long long>(c->tiles_cap[3], INT32_MAX));
+        va.n_tiles = &c->ctl->n_active[n_levels - 1];
+        va.tps = uint32_t(S / px_of[n_levels - 1]);
+        va.ctl = c->ctl;
+        va.queue = &c->ctl->queue[q++];
+        va.n_slots = n_slots;
+        va.z = z;
+        launch_eval_voxels(dim, va, mat, c->sm_count * cached_occupancy(c, 1, dim, false, n_slots), s);
+        tm.mark();
+    }
+    if (dim == 3) {
+        NormalsArgs na = {};
+        na.arena = c->arena;
+        na.image = c->filled[3];
+        na.normals = c->normals;
+        na.size = S;
+        na.y_begin = c->row_begin * 64;
+        na.y_end = c->row_end * 64;
+        na.tiles0 = c->tiles[0];
+        na.tiles1 = c->tiles[1];
+        na.tiles2 = c->tiles[2];
+        na.ctl = c->ctl;
+        na.queue = &c->ctl->queue[q++];
+        na.n_slots = n_slots;
+        launch_normals(na, m4, c->sm_count * cached_occupancy(c, 2, 3, false, n_slots), s);
+        tm.mark();
+    }
+    MPRB_CUDA(cudaMemcpyAsync(c->ctl_host, c->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
+    cudaEventRecord(c->ev_end, s);
+    c->stats.n_launches = tm.n - 1;
+    MPRB_CUDA(cudaGetLastError());
+    return MPRB_OK;
+}
+
+// Waits for the frame and publishes the counters.
+int finish(mprb_ctx* c, int dim) {
+    MPRB_CUDA(cudaStreamSynchronize(c->stream));
+    const FrameCtl& f = *c->ctl_host;
+    mprb_frame_stats& st = c->stats;
+    const int n_launches = st.n_launches;
+    memset(&st, 0, sizeof(st));
+    st.n_launches = n_launches;
+    const int n_levels = dim == 3 ? 3 : 2;
+    for (int i = 0; i < 3; ++i) {
+        st.n_active[i] = f.n_active[i];
+        st.i_tiles[i] = f.stats[ST_I_TILES + i];
+        st.i_cells[i] = f.stats[ST_I_CELLS + i];
+        st.p_tiles[i] = f.stats[ST_P_TILES + i];
+        st.p_cells[i] = f.stats[ST_P_CELLS + i];
+        st.p_kept[i] = f.stats[ST_P_KEPT + i];
+    }
+    st.f_tiles = f.stats[ST_F_TILES];
+    st.f_cells = f.stats[ST_F_CELLS];
+    st.n_pixels = f.stats[ST_N_PIXELS];
+    st.n_cells = f.stats[ST_N_CELLS];
+    st.overflow = f.overflow;
+    cudaEventElapsedTime(&st.gpu_ms, c->ev_begin, c->ev_end);
+    if (c->timing) {
+        for (int i = 0; i < n_launches && i < kMaxLaunches; ++i)
+            cudaEventElapsedTime(&st.kernel_ms[i], c->ev_k[i], c->ev_k[i + 1]);
+    }
+    // Host-visible mirrors of the reference's members.
+    const int tps0 = c->size / 64;
+    c->tile_array_size[0] = dim == 3 ? uint64_t(tps0) * tps0 * tps0 : uint64_t(tps0) * tps0;
+    if (dim == 3) {
+        c->tile_array_size[1] = uint64_t(f.n_active[0]) * 64;
+        c->tile_array_size[2] = uint64_t(f.n_active[1]) * 64;
+        c->tile_array_size[3] = uint64_t(f.n_active[2]);
+    } else {
+        c->tile_array_size[2] = uint64_t(f.n_active[0]) * 64;
+        c->tile_array_size[3] = uint64_t(f.n_active[1]);
+    }
+    st.tape_index = f.tape_cursor;
+    *c->tape_index = f.tape_cursor;
+    *c->num_active_tiles = f.n_active[n_levels - 1];
+    if (f.overflow)
+        return fail(MPRB_E_OVERFLOW, "tile list overflow (mask 0x%x): more than %lld tiles at one level",
+                    f.overflow, kMaxStageTiles);
+    return MPRB_OK;
+}
+
+}  // namespace
+
+////////////////////////////////////////////////////////////////////////////////
+
+extern "C" {
+
+const char* mprb_last_error(void) { return g_error.c_str(); }
+const char* mprb_version(void) { return "mprb 0.1 (sm_100a)"; }
+
+int mprb_ctx_create(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx** out) {
+    if (!out) return fail(MPRB_E_ARG, "null out pointer");
+    *out = nullptr;
+    if (image_size_px < 64 || image_size_px % 64 != 0)
+        return fail(MPRB_E_ARG, "image_size_px must be a positive multiple of 64 (got %d)", image_size_px);
+    int device = opts ? opts->device : -1;
+    if (device < 0) MPRB_CUDA(cudaGetDevice(&device));
+    MPRB_CUDA(cudaSetDevice(device));
+
+    mprb_ctx* c = new mprb_ctx;
+    c->device = device;
+    c->size = image_size_px;
+    const int tps0 = image_size_px / 64;
+    c->row_begin = opts ? opts->row_begin : 0;
+    c->row_end = (opts && opts->row_end > 0) ? opts->row_end : tps0;
+    if (c->row_begin < 0 || c->row_end > tps0 || c->row_begin >= c->row_end) {
+        delete c;
+        return fail(MPRB_E_ARG, "tile-row band [%d, %d) is outside [0, %d)", opts ? opts->row_begin : 0,
+                    opts ? opts->row_end : 0, tps0);
+    }
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    init_kernels(max_smem);
+
+    auto bail = [&](cudaError_t e, const char* what) {
+        fail(MPRB_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+        mprb_ctx_destroy(c);
+        return MPRB_E_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(e, "cudaStreamCreate");
+    cudaEventCreate(&c->ev_begin);
+    cudaEventCreate(&c->ev_end);
+    for (auto& ev : c->ev_k) cudaEventCreate(&ev);
+
+    // Filled images: (S/64)^2, (S/16)^2, (S/4)^2, S^2 (context.cpp:21-26)
+    for (int i = 0; i < 4; ++i) {
+        const size_t side = size_t(image_size_px) / (64 >> (2 * i));
+        if ((e = managed_alloc(&c->filled[i], side * side, device)) != cudaSuccess)
+            return bail(e, "filled image");
+    }
+    if ((e = managed_alloc(&c->normals, size_t(image_size_px) * image_size_px, device)) != cudaSuccess)
+        return bail(e, "normals");
+    const long long chunks = (opts && opts->num_subtapes > 0) ? opts->num_subtapes : 640000;
+    c->arena_cells = chunks * kChunk;
+    if (c->arena_cells > INT32_MAX) {
+        mprb_ctx_destroy(c);
+        return fail(MPRB_E_ARG, "num_subtapes too large for 32-bit tape indices");
+    }
+    if ((e = managed_alloc(&c->arena, size_t(c->arena_cells) + kChunk, device)) != cudaSuccess)
+        return bail(e, "tape arena");
+    // Host-side mirrors of two device counters (the device copies live in FrameCtl)
+    if ((e = cudaMallocManaged(&c->tape_index, sizeof(int32_t))) != cudaSuccess) return bail(e, "tape_index");
+    if ((e = cudaMallocManaged(&c->num_active_tiles, sizeof(int32_t))) != cudaSuccess)
+        return bail(e, "num_active_tiles");
+    *c->tape_index = 0;
+    *c->num_active_tiles = 0;
+    // Stage 0 holds every 64^3 tile of the volume (context.cpp:39-43)
+    const long long count0 = (long long)tps0 * tps0 * tps0;
+    c->tiles_cap[0] = 0;
+    {
+        TileNode* p = nullptr;
+        if ((e = managed_alloc(&p, size_t(count0), device)) != cudaSuccess) return bail(e, "stage 0 tiles");
+        c->tiles[0] = p;
+        c->tiles_cap[0] = count0;
+        if ((e = cudaMalloc(&c->active_list[0], sizeof(int32_t) * size_t(count0))) != cudaSuccess)
+            return bail(e, "active list");
+    }
+    if ((e = cudaMalloc(&c->ctl, sizeof(FrameCtl))) != cudaSuccess) return bail(e, "control block");
+    if ((e = cudaMallocHost(&c->ctl_host, sizeof(FrameCtl))) != cudaSuccess) return bail(e, "pinned control block");
+    memset(c->ctl_host, 0, sizeof(FrameCtl));
+    cudaDeviceSynchronize();
+    *out = c;
+    return MPRB_OK;
+}
+
+void mprb_ctx_destroy(mprb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 4; ++i) {
+        if (c->filled[i]) cudaFree(c->filled[i]);
+        if (c->tiles[i]) cudaFree(c->tiles[i]);
+    }
+    for (int i = 0; i < 3; ++i) if (c->active_list[i]) cudaFree(c->active_list[i]);
+    if (c->arena) cudaFree(c->arena);
+    if (c->tape_index) cudaFree(c->tape_index);
+    if (c->num_active_tiles) cudaFree(c->num_active_tiles);
+    if (c->normals) cudaFree(c->normals);
+    if (c->ctl) cudaFree(c->ctl);
+    if (c->ctl_host) cudaFreeHost(c->ctl_host);
+    if (c->stage_cells) cudaFreeHost(c->stage_cells);
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
+    for (auto& ev : c->ev_k) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int mprb_ctx_buffers(mprb_ctx* c, mprb_buffers* out) {
+    if (!c || !out) return fail(MPRB_E_ARG, "null argument");
+    out->image_size_px = c->size;
+    for (int i = 0; i < 4; ++i) {
+        out->filled[i] = c->filled[i];
+        out->tiles[i] = reinterpret_cast<mprb_tile_node*>(c->tiles[i]);
+        out->tile_array_size[i] = c->tile_array_size[i];
+    }
+    out->tape_data = c->arena;
+    out->tape_index = c->tape_index;
+    out->num_active_tiles = c->num_active_tiles;
+    out->normals = c->normals;
+    return MPRB_OK;
+}
+
+int mprb_ctx_set_timing(mprb_ctx* c, int enabled) {
+    if (!c) return fail(MPRB_E_ARG, "null context");
+    c->timing = enabled != 0;
+    return MPRB_OK;
+}
+
+int mprb_tape_create(const uint64_t* host_cells, int32_t n_cells, mprb_tape** out) {
+    if (!out) return fail(MPRB_E_ARG, "null out pointer");
+    *out = nullptr;
+    if (int e = validate_tape(host_cells, n_cells)) return e;
+    mprb_tape* t = new mprb_tape;
+    cudaError_t e = cudaMallocManaged(&t->cells, sizeof(uint64_t) * size_t(n_cells));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(t->cells, host_cells, sizeof(uint64_t) * size_t(n_cells), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (t->cells) cudaFree(t->cells);
+        delete t;
+        return fail(MPRB_E_CUDA, "tape upload: %s", cudaGetErrorString(e));
+    }
+    t->length = n_cells;
+    t->n_slots = tape_num_slots(host_cells, n_cells);
+    *out = t;
+    return MPRB_OK;
+}
+
+void mprb_tape_destroy(mprb_tape* t) {
+    if (!t) return;
+    if (t->cells) cudaFree(t->cells);
+    delete t;
+}
+
+const uint64_t* mprb_tape_data(const mprb_tape* t) { return t ? t->cells : nullptr; }
+int32_t mprb_tape_length(const mprb_tape* t) { return t ? t->length : 0; }
+int32_t mprb_tape_num_slots(const mprb_tape* t) { return t ? t->n_slots : 0; }
+
+int mprb_render2d(mprb_ctx* c, const mprb_tape* t, const float mat3[9], float z) {
+    if (!c || !t || !mat3) return fail(MPRB_E_ARG, "null argument");
+    if (int e = render(c, 2, t->cells, t->length, false, t->n_slots, mat3, z)) return e;
+    return finish(c, 2);
+}
+
+int mprb_render3d(mprb_ctx* c, const mprb_tape* t, const float mat4[16]) {
+    if (!c || !t || !mat4) return fail(MPRB_E_ARG, "null argument");
+    if (int e = render(c, 3, t->cells, t->length, false, t->n_slots, mat4, 0.0f)) return e;
+    return finish(c, 3);
+}
+
+int mprb_render2d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
+                       const float mat3[9], float z, int32_t* image_out) {
+    if (!c || !mat3 || !image_out) return fail(MPRB_E_ARG, "null argument");
+    if (int e = validate_tape(host_cells, n_cells)) return e;
+    if (int e = render(c, 2, host_cells, n_cells, true, tape_num_slots(host_cells, n_cells), mat3, z)) return e;
+    const size_t n = size_t(c->size) * c->size;
+    MPRB_CUDA(cudaMemcpyAsync(image_out, c->filled[3], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    return finish(c, 2);
+}
+
+int mprb_render3d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
+                       const float mat4[16], int32_t* depth_out, uint32_t* normals_out) {
+    if (!c || !mat4 || !depth_out) return fail(MPRB_E_ARG, "null argument");
+    if (int e = validate_tape(host_cells, n_cells)) return e;
+    if (int e = render(c, 3, host_cells, n_cells, true, tape_num_slots(host_cells, n_cells), mat4, 0.0f)) return e;
+    const size_t n = size_t(c->size) * c->size;
+    MPRB_CUDA(cudaMemcpyAsync(depth_out, c->filled[3], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (normals_out)
+        MPRB_CUDA(cudaMemcpyAsync(normals_out, c->normals, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    return finish(c, 3);
+}
+
+int mprb_frame_stats_get(mprb_ctx* c, mprb_frame_stats* out) {
+    if (!c || !out) return fail(MPRB_E_ARG, "null argument");
+    *out = c->stats;
+    return MPRB_OK;
+}
+
+int mprb_tape_from_frep(const uint8_t* bytes, size_t n_bytes, int simplify,
+                        uint64_t** cells_out, int32_t* n_cells_out, int32_t* n_slots_out) {
+    if (!bytes || !cells_out || !n_cells_out) return fail(MPRB_E_ARG, "null argument");
+    std::istringstream in(std::string(reinterpret_cast<const char*>(bytes), n_bytes), std::ios::binary);
+    libfive::Cache::setSimplify(simplify != 0);
+    auto archive = libfive::Archive::deserialize(in);
+    libfive::Cache::setSimplify(true);
+    if (archive.shapes.empty() || !archive.shapes.front().tree.id())
+        return fail(MPRB_E_PARSE, "no shape in archive");
+    int n_slots = 0;
+    const auto tape = pack_tape(archive.shapes.front().tree, &n_slots);
+    uint64_t* p = static_cast<uint64_t*>(malloc(sizeof(uint64_t) * tape.size()));
+    if (!p) return fail(MPRB_E_ARG, "out of memory");
+    memcpy(p, tape.data(), sizeof(uint64_t) * tape.size());
+    *cells_out = p;
+    *n_cells_out = int32_t(tape.size());
+    if (n_slots_out) *n_slots_out = n_slots;
+    return MPRB_OK;
+}
+
+void mprb_free(void* p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,920 @@
+// mprb device kernels (sm_100a).
+//
+// One frame = a fixed stream of persistent kernels; no host round trips.
+//
+//   k_eval_tiles<DIM, ROOT>   interval pass over one subdivision level:
+//       a warp owns 32 tiles that share one tape (at the root level: 32
+//       consecutive top-level tiles; below: half of a parent's 64 children),
+//       so the clause stream and the opcode switch are warp-uniform.  Each
+//       lane keeps its tile's slot values in shared memory as [slot][lane]
+//       (bank-conflict free), records min/max verdicts, classifies the tile,
+//       and - if ambiguous - emits its own shortened tape into the arena in
+//       the reference's chunked format while the warp walks the tape backward.
+//       Child coordinates, the projective transform, the occlusion pre-mask
+//       and the TileNode write-back are fused in.
+//   k_rank_tiles              occlusion post-mask + compaction of survivors
+//   k_upsample_filled         filled image -> next level's image
+//   k_eval_voxels<DIM>        float pass: a warp owns one 64-sample tile,
+//                             two samples per lane
+//   k_normals                 per-pixel gradient pass, lanes grouped by tape
+//
+// Behaviour (what is computed, bit for bit) follows the reference kernels in
+// reference src/context.cu; line numbers are cited at each step.  How it is
+// scheduled (work units, memory layout, fusion, queues) is specific to this
+// implementation.
+#include <cstdint>
+
+#include "common.cuh"
+#include "deriv.cuh"
+#include "ival.cuh"
+#include "kernels.cuh"
+
+namespace mprb {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// One lane claims the next work item for its warp.
+__device__ __forceinline__ int warp_next(int32_t* head) {
+    int v = 0;
+    if (lane_id() == 0) v = atomicAdd(head, 1);
+    return __shfl_sync(kFull, v, 0);
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned v) {
+    return __reduce_add_sync(kFull, v);
+}
+
+__device__ __forceinline__ uint64_t make_jump(int32_t delta) {
+    return uint64_t(OP_JUMP) | (uint64_t(uint32_t(delta)) << 32);
+}
+
+// 128-bit per-lane set of live slots, kept in four registers.
+struct SlotSet {
+    uint32_t w0, w1, w2, w3;
+    __device__ __forceinline__ void clear() { w0 = w1 = w2 = w3 = 0; }
+    __device__ __forceinline__ bool test(uint32_t s) const {
+        const uint32_t k = s >> 5;
+        const uint32_t v = (k == 0) ? w0 : (k == 1) ? w1 : (k == 2) ? w2 : w3;
+        return (v >> (s & 31)) & 1u;
+    }
+    __device__ __forceinline__ void set(uint32_t s) {
+        const uint32_t k = s >> 5, m = 1u << (s & 31);
+        w0 |= (k == 0) ? m : 0u;
+        w1 |= (k == 1) ? m : 0u;
+        w2 |= (k == 2) ? m : 0u;
+        w3 |= (k == 3) ? m : 0u;
+    }
+    __device__ __forceinline__ void reset(uint32_t s) {
+        const uint32_t k = s >> 5, m = ~(1u << (s & 31));
+        w0 &= (k == 0) ? m : ~0u;
+        w1 &= (k == 1) ? m : ~0u;
+        w2 &= (k == 2) ? m : ~0u;
+        w3 &= (k == 3) ? m : ~0u;
+    }
+};
+
+// a*x + b*y + c*z + d with the reference build's rounding sequence
+// (SASS of calculate_voxels / eval_pixels_d: FMUL b*y; FFMA a*x+.; FFMA c*z+.; FADD d).
+__device__ __forceinline__ float dot3(float a, float x, float b, float y, float c, float z, float d) {
+    return __fadd_rn(__fmaf_rn(c, z, __fmaf_rn(a, x, __fmul_rn(b, y))), d);
+}
+// a*x + b*y + c  (SASS of calculate_pixels: FMUL b*y; FFMA a*x+.; FADD c)
+__device__ __forceinline__ float dot2(float a, float x, float b, float y, float c) {
+    return __fadd_rn(__fmaf_rn(a, x, __fmul_rn(b, y)), c);
+}
+// ((p + 0.5) * recip - 0.5) * 2 -> FADD; FFMA; FADD t+t  (context.cu:734-736)
+__device__ __forceinline__ float sample_coord(int p, float recip) {
+    const float t = __fmaf_rn(__fadd_rn(float(p), 0.5f), recip, -0.5f);
+    return __fadd_rn(t, t);
+}
+
+// (p / tiles_per_side - 0.5) * 2  (context.cu:93-98)
+__device__ __forceinline__ float tile_edge(int p, float ftps) {
+    return __fmul_rn(__fsub_rn(__fdiv_rn(float(p), ftps), 0.5f), 2.0f);
+}
+
+template <int N> struct MatOf;
+template <> struct MatOf<2> { typedef Mat3 type; };
+template <> struct MatOf<3> { typedef Mat4 type; };
+
+}  // namespace
+
+////////////////////////////////////////////////////////////////////////////////
+// Interval pass
+
+template <int DIM, bool ROOT>
+__global__ void __launch_bounds__(kEvalThreads)
+k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
+{
+    extern __shared__ float2 s_slots[];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    // Slot s of this lane's tile lives at slots[s * 32].
+    float2* const slots = s_slots + size_t(warp) * a.n_slots * 32 + lane;
+
+    uint64_t* const arena = a.arena;
+    uint32_t choices[kMaxChoices / 16];   // 2 bits per recorded min/max verdict
+
+    const int n_items = ROOT ? (a.count0 + 31) / 32 : 2 * min(*a.n_parents, a.tiles_cap / 64);
+    const uint32_t tps = a.tps;
+    const uint64_t root_hdr = arena[0];   // axis slots always come from the root header
+                                          // (context.cu:211-213)
+    for (;;) {
+        const int item = warp_next(a.queue);
+        if (item >= n_items) break;
+
+        // ---- which tile does this lane own? -------------------------------------
+        int tile_index;     // where its TileNode lives in a.tiles
+        int tape;           // arena index of the tape header (warp-uniform)
+        int sx, sy, sz = 0;
+        bool valid = true, inband = true;
+        if (ROOT) {
+            int t = item * 32 + lane;
+            if (DIM == 3) t = a.count0 - 1 - t;      // highest z first: better culling
+            valid = (t >= 0) && (t < a.count0);
+            tile_index = t;
+            tape = 0;
+            const int tt = valid ? t : 0;
+            sx = tt % tps;
+            sy = (tt / tps) % tps;
+            if (DIM == 3) sz = (tt / tps) / tps;
+            inband = (sy >= a.row_begin) && (sy < a.row_end);
+        } else {
+            const int rank = item >> 1;
+            const int sub = ((item & 1) << 5) | lane;
+            const TileNode parent = a.ptiles[a.pactive[rank]];
+            tape = parent.tape;
+            tile_index = rank * 64 + sub;
+            const int pp = parent.position;
+            const int px = pp % a.ptps, py = (pp / a.ptps) % a.ptps;
+            if (DIM == 3) {   // 4x4x4 children, sub = x + 4y + 16z (context.cu:579-588)
+                const int pz = (pp / a.ptps) / a.ptps;
+                sx = px * 4 + (sub & 3);
+                sy = py * 4 + ((sub >> 2) & 3);
+                sz = pz * 4 + (sub >> 4);
+            } else {          // 8x8 children, sub = x + 8y (context.cu:612-617)
+                sx = px * 8 + (sub & 7);
+                sy = py * 8 + (sub >> 3);
+            }
+        }
+        const int position = sx + sy * tps + (DIM == 3 ? sz * tps * tps : 0);
+        const int img_index = sx + sy * tps;
+
+        // Occlusion pre-mask (first mask_filled_tiles, context.cu:1335, :486-494)
+        bool alive = valid && inband;
+        if (DIM == 3 && alive) {
+            if (__ldcg(&a.image[img_index]) > sz) alive = false;
+        }
+        if (!__any_sync(kFull, alive)) {
+            if (valid) {
+                a.tiles[tile_index].position = -1;
+                a.tiles[tile_index].tape = tape;
+                a.tiles[tile_index].next = -1;
+            }
+            continue;
+        }
+
+        // ---- tile box -> transformed intervals (context.cu:78-159) ---------------
+        {
+            const float ftps = float(tps);
+            const ival ix = iv(tile_edge(sx, ftps), tile_edge(sx + 1, ftps));
+            const ival iy = iv(tile_edge(sy, ftps), tile_edge(sy + 1, ftps));
+            ival X, Y, Z;
+            if (DIM == 3) {
+                const ival iz = iv(tile_edge(sz, ftps), tile_edge(sz + 1, ftps));
+                const float* m = mat.d;   // column major: m(r, c) = m[c * 4 + r]
+                ival r[4];
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    r[i] = iv_add(iv_add(iv_add(iv_mul(ix, m[i]), iv_mul(iy, m[4 + i])),
+                                         iv_mul(iz, m[8 + i])), m[12 + i]);
+                }
+                X = iv_div(r[0], r[3]);
+                Y = iv_div(r[1], r[3]);
+                Z = iv_div(r[2], r[3]);
+            } else {
+                const float* m = mat.d;   // m(r, c) = m[c * 3 + r]
+                ival r[3];
+                #pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    r[i] = iv_add(iv_add(iv_mul(ix, m[i]), iv_mul(iy, m[3 + i])), m[6 + i]);
+                }
+                X = iv_div(r[0], r[2]);
+                Y = iv_div(r[1], r[2]);
+                Z = iv(a.z, a.z);
+            }
+            const uint32_t h = uint32_t(root_hdr);
+            slots[((h >> 8) & 0xff) * 32] = X;
+            slots[((h >> 16) & 0xff) * 32] = Y;
+            slots[(h >> 24) * 32] = Z;
+        }
+
+        // ---- forward walk (context.cu:223-287) -------------------------------------
+        int pos = tape;
+        int n_choice = 0;          // warp-uniform: how many min/max clauses seen so far
+        uint32_t cw = 0;           // verdict word under construction
+        bool any_choice = false;
+        unsigned cells = 0;
+        uint64_t d_next = arena[pos + 1];
+        uint64_t d;
+        for (;;) {
+            ++pos;
+            d = d_next;
+            const uint32_t w = uint32_t(d);
+            const uint32_t op = w & 0xff;
+            if (op == OP_END) break;
+            ++cells;
+            if (op == OP_JUMP) {
+                pos += int32_t(d >> 32);
+                d_next = arena[pos + 1];
+                continue;
+            }
+            d_next = arena[pos + 1];
+            const uint32_t i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
+            const float imm = __uint_as_float(uint32_t(d >> 32));
+            const ival L = slots[i_lhs * 32];
+            const ival R = slots[i_rhs * 32];
+            ival o;
+            int c = 0;
+            switch (op) {
+                case OP_SQUARE: o = iv_square(L); break;
+                case OP_SQRT:   o = iv_sqrt(L); break;
+                case OP_NEG:    o = iv_neg(L); break;
+                case OP_SIN:    o = iv_sin(L); break;
+                case OP_COS:    o = iv_cos(L); break;
+                case OP_ASIN:   o = iv_asin(L); break;
+                case OP_ACOS:   o = iv_acos(L); break;
+                case OP_ATAN:   o = iv_atan(L); break;
+                case OP_EXP:    o = iv_exp(L); break;
+                case OP_ABS:    o = iv_abs(L); break;
+                case OP_LOG:    o = iv_log(L); break;
+                case OP_ADD_LI: o = iv_add(L, imm); break;
+                case OP_ADD_LR: o = iv_add(L, R); break;
+                case OP_MUL_LI: o = iv_mul(L, imm); break;
+                case OP_MUL_LR: o = iv_mul(L, R); break;
+                case OP_MIN_LI: o = iv_min(L, iv(imm, imm), c); break;
+                case OP_MIN_LR: o = iv_min(L, R, c); break;
+                case OP_MAX_LI: o = iv_max(L, iv(imm, imm), c); break;
+                case OP_MAX_LR: o = iv_max(L, R, c); break;
+                case OP_SUB_LI: o = iv_sub(L, imm); break;
+                case OP_SUB_IR: o = iv_sub(imm, R); break;
+                case OP_SUB_LR: o = iv_sub(L, R); break;
+                case OP_DIV_LI: o = iv_div(L, imm); break;
+                case OP_DIV_IR: o = iv_div(imm, R); break;
+                case OP_DIV_LR: o = iv_div(L, R); break;
+                case OP_COPY_IMM: o = iv(imm, imm); break;
+                case OP_COPY_LHS: o = L; break;
+                case OP_COPY_RHS: o = R; break;
+                default: o = L; break;
+            }
+            if (op >= OP_MIN_LI && op <= OP_MAX_LR) {
+                // Verdicts past kMaxChoices are not recorded (context.cu:257-259)
+                cw |= uint32_t(c) << ((n_choice & 15) * 2);
+                if ((n_choice & 15) == 15) {
+                    if (n_choice < kMaxChoices) choices[n_choice >> 4] = cw;
+                    cw = 0;
+                }
+                ++n_choice;
+                any_choice |= (c != 0);
+            }
+            slots[i_out * 32] = o;
+        }
+        if ((n_choice & 15) && n_choice < kMaxChoices) choices[n_choice >> 4] = cw;
+        const uint64_t end_cell = d;                       // {0, result slot}
+        const uint32_t i_result = (uint32_t(end_cell) >> 8) & 0xff;
+        const ival result = slots[i_result * 32];
+
+        // ---- classify (context.cu:289-321) -----------------------------------------
+        int out_position = -1;
+        bool pushing = false;
+        if (alive) {
+            if (result.x > 0.0f) {
+                // empty
+            } else if (DIM == 3 && __ldcg(&a.image[img_index]) > sz) {
+                // hidden below a filled tile that landed meanwhile
+            } else if (result.y < 0.0f) {
+                if (DIM == 3) atomicMax(&a.image[img_index], sz);
+                else a.image[img_index] = 1;
+            } else {
+                out_position = position;
+                pushing = any_choice;
+            }
+        }
+        int out_tape = tape;
+
+        // ---- statistics ----------------------------------------------------------------
+        {
+            const unsigned n_alive = __popc(__ballot_sync(kFull, alive));
+            if (lane == 0) {
+                atomicAdd(&a.ctl->stats[ST_I_TILES + a.level], (unsigned long long)n_alive);
+                atomicAdd(&a.ctl->stats[ST_I_CELLS + a.level], (unsigned long long)n_alive * cells);
+            }
+        }
+
+        // ---- tape push: backward mark & sweep (context.cu:323-458) ---------------------
+        if (__any_sync(kFull, pushing)) {
+            const int cap = a.arena_cap;
+            SlotSet live;
+            live.clear();
+            live.set(i_result);
+            int o_idx = 0, o_off = 0;
+            unsigned kept = 0;
+            if (pushing) {
+                if (*(volatile int32_t*)a.tape_index >= cap) {
+                    pushing = false;
+                } else {
+                    o_idx = atomicAdd(a.tape_index, kChunk);
+                    if (o_idx + kChunk >= cap) {
+                        pushing = false;
+                    } else {
+                        o_off = kChunk - 1;
+                        arena[o_idx + o_off] = end_cell;
+                        kept = 1;
+                    }
+                }
+            }
+            const bool pushed0 = pushing;
+            unsigned bcells = 0;
+            int ci = n_choice;
+            int cw_index = -1;
+            uint32_t cwb = 0;
+            for (;;) {
+                d = arena[--pos];
+                const uint32_t w = uint32_t(d);
+                const uint32_t op = w & 0xff;
+                if (op == OP_END) break;
+                ++bcells;
+                if (op == OP_JUMP) {
+                    pos += int32_t(d >> 32);
+                    continue;
+                }
+                const bool has_choice = (op >= OP_MIN_LI && op <= OP_MAX_LR);
+                int choice = 0;
+                if (has_choice) {
+                    --ci;
+                    if (ci < kMaxChoices) {
+                        if ((ci >> 4) != cw_index) {
+                            cw_index = ci >> 4;
+                            cwb = choices[cw_index];
+                        }
+                        choice = (cwb >> ((ci & 15) * 2)) & 3;
+                    }
+                }
+                const uint32_t i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
+                if (pushing && live.test(i_out)) {
+                    // Reserve the cell; open a new chunk when this one is used up.
+                    --o_off;
+                    bool ok = true;
+                    if (o_off == 0) {
+                        const int prev = o_idx;
+                        if (*(volatile int32_t*)a.tape_index >= cap) {
+                            ok = false;
+                        } else {
+                            o_idx = atomicAdd(a.tape_index, kChunk);
+                            if (o_idx + kChunk >= cap) {
+                                ok = false;
+                            } else {
+                                o_off = kChunk - 1;
+                                const int32_t delta = prev - (o_idx + o_off);
+                                arena[o_idx + o_off] = make_jump(delta);   // forward link
+                                arena[prev] = make_jump(-delta);           // backward link
+                                --o_off;
+                                kept += 2;
+                            }
+                        }
+                    }
+                    if (!ok) {
+                        pushing = false;   // arena exhausted: keep the parent tape
+                    } else {
+                        live.reset(i_out);
+                        uint64_t e = d;
+                        bool emit = true;
+                        if (choice == 0) {
+                            if (i_lhs) live.set(i_lhs);
+                            if (i_rhs) live.set(i_rhs);
+                        } else if (choice == 1) {
+                            live.set(i_lhs);
+                            if (i_lhs == i_out) emit = false;
+                            else e = (d & ~0xffull) | OP_COPY_LHS;
+                        } else if (choice == 2) {
+                            if (i_rhs) {
+                                live.set(i_rhs);
+                                if (i_rhs == i_out) emit = false;
+                                else e = (d & ~0xffull) | OP_COPY_RHS;
+                            } else {
+                                e = (d & ~0xffull) | OP_COPY_IMM;
+                            }
+                        }
+                        if (emit) {
+                            arena[o_idx + o_off] = e;
+                            ++kept;
+                        } else {
+                            ++o_off;   // give the reserved cell back
+                        }
+                    }
+                }
+            }
+            // `d` is the header cell the walk stopped on; it goes in front.
+            if (pushing) {
+                --o_off;
+                arena[o_idx + o_off] = d;
+                ++kept;
+                out_tape = o_idx + o_off;
+            }
+            {
+                const unsigned n_push = __popc(__ballot_sync(kFull, pushed0));
+                const unsigned long long k_sum = warp_sum(pushed0 ? kept : 0u);
+                if (lane == 0) {
+                    atomicAdd(&a.ctl->stats[ST_P_TILES + a.level], (unsigned long long)n_push);
+                    atomicAdd(&a.ctl->stats[ST_P_CELLS + a.level], (unsigned long long)n_push * bcells);
+                    atomicAdd(&a.ctl->stats[ST_P_KEPT + a.level], k_sum);
+                }
+            }
+        }
+
+        if (valid) {
+            a.tiles[tile_index].position = out_position;
+            a.tiles[tile_index].tape = out_tape;
+            a.tiles[tile_index].next = -1;
+        }
+    }
+}
+
+////////////////////////////////////////////////////////////////////////////////
+// Post-mask + compaction (mask_filled_tiles #2, assign_next_nodes,
+// subdivide / copy_active_tiles bookkeeping; context.cu:471-551, :637-651)
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_rank_tiles(const RankArgs a)
+{
+    const int n_tiles = a.n_parents ? 64 * min(*a.n_parents, a.tiles_cap / 64) : a.count0;
+    const int lane = lane_id();
+    const int stride = gridDim.x * blockDim.x;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n_tiles; base += stride) {
+        const int t = base + lane;
+        bool active = false;
+        TileNode node = {-1, 0, -1};
+        if (t < n_tiles) {
+            node = a.tiles[t];
+            if (node.position != -1) {
+                active = true;
+                if (DIM == 3) {
+                    const int xy = node.position % (a.tps * a.tps);
+                    const int z = node.position / (a.tps * a.tps);
+                    if (a.image[xy] > z) {
+                        active = false;
+                        a.tiles[t].position = -1;
+                    }
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(kFull, active);
+        int rank_base = 0;
+        if (lane == 0 && m) rank_base = atomicAdd(a.n_active, __popc(m));
+        rank_base = __shfl_sync(kFull, rank_base, 0);
+        if (t < n_tiles) {
+            int next = -1;
+            if (active) {
+                const int rank = rank_base + __popc(m & ((1u << lane) - 1));
+                const long long need = a.last_level ? (long long)rank + 1 : ((long long)rank + 1) * 64;
+                if (need > a.next_cap) {
+                    // Next stage's tile array is too small: flag it; the host
+                    // grows the array and renders the frame again.
+                    atomicOr(&a.ctl->overflow, 1 << a.level);
+                } else if (a.last_level) {
+                    // Compact list for the float pass; `next` stays -1 (copy_active_tiles)
+                    a.out_tiles[rank].position = node.position;
+                    a.out_tiles[rank].tape = node.tape;
+                    a.out_tiles[rank].next = -1;
+                }
+                if (!a.last_level) {
+                    a.active_list[rank] = t;
+                    next = rank;
+                }
+            }
+            a.tiles[t].next = next;
+        }
+    }
+}
+
+// Filled image of one level -> the next (copy_filled_{2d,3d}, context.cu:664-692).
+// Writes every pixel, so the destination needs no separate clear.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_upsample_filled(const int32_t* __restrict__ prev, int32_t* __restrict__ image, int size)
+{
+    constexpr int F = (DIM == 3) ? 4 : 8;
+    const int n = size * size;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int x = i % size, y = i / size;
+        const int32_t t = prev[x / F + (y / F) * (size / F)];
+        image[i] = t ? (DIM == 3 ? t * 4 + 3 : 1) : 0;
+    }
+}
+
+////////////////////////////////////////////////////////////////////////////////
+// Float pass (calculate_voxels / calculate_pixels + eval_voxels_f,
+// context.cu:707-964)
+
+template <int DIM>
+__global__ void __launch_bounds__(kEvalThreads)
+k_eval_voxels(const EvalVoxelsArgs a, const typename MatOf<DIM>::type mat)
+{
+    extern __shared__ float2 s_slots[];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    float2* const slots = s_slots + size_t(warp) * a.n_slots * 32 + lane;
+    const uint64_t* const arena = a.arena;
+    const uint32_t h = uint32_t(arena[0]);
+    const int n_items = min(*a.n_tiles, a.tiles_cap);
+    const uint32_t tps = a.tps;
+
+    for (;;) {
+        const int item = warp_next(a.queue);
+        if (item >= n_items) break;
+        const TileNode tile = a.tiles[item];
+        const int tx = tile.position % tps, ty = (tile.position / tps) % tps;
+
+        int px, py, pz = 0, img_a, img_b;
+        float2 X, Y, Z;
+        bool alive = true;
+        if (DIM == 3) {
+            const int tz = (tile.position / tps) / tps;
+            const int size = tps * 4;
+            px = tx * 4 + (lane & 3);
+            py = ty * 4 + ((lane >> 2) & 3);
+            pz = tz * 4 + (lane >> 4);          // second sample sits at pz + 2
+            img_a = img_b = px + py * size;
+            // This column already shows something at least as high (context.cu:852-864)
+            if (__ldcg(&a.image[img_a]) >= pz + 2) alive = false;
+            if (!__any_sync(kFull, alive)) continue;
+
+            const float recip = 1.0f / float(tps * 4u);
+            const float fx = sample_coord(px, recip), fy = sample_coord(py, recip);
+            const float fza = sample_coord(pz, recip), fzb = sample_coord(pz + 2, recip);
+            const float* m = mat.d;
+            const float wa = dot3(m[3], fx, m[7], fy, m[11], fza, m[15]);
+            const float wb = dot3(m[3], fx, m[7], fy, m[11], fzb, m[15]);
+            X = make_float2(dot3(m[0], fx, m[4], fy, m[8], fza, m[12]) / wa,
+                            dot3(m[0], fx, m[4], fy, m[8], fzb, m[12]) / wb);
+            Y = make_float2(dot3(m[1], fx, m[5], fy, m[9], fza, m[13]) / wa,
+                            dot3(m[1], fx, m[5], fy, m[9], fzb, m[13]) / wb);
+            Z = make_float2(dot3(m[2], fx, m[6], fy, m[10], fza, m[14]) / wa,
+                            dot3(m[2], fx, m[6], fy, m[10], fzb, m[14]) / wb);
+        } else {
+            const int size = tps * 8;
+            px = tx * 8 + (lane & 7);
+            py = ty * 8 + (lane >> 3);          // second sample sits at py + 4
+            img_a = px + py * size;
+            img_b = px + (py + 4) * size;
+            const float recip = 1.0f / float(tps * 8u);
+            const float fx = sample_coord(px, recip);
+            const float fya = sample_coord(py, recip), fyb = sample_coord(py + 4, recip);
+            const float* m = mat.d;
+            const float wa = dot2(m[2], fx, m[5], fya, m[8]);
+            const float wb = dot2(m[2], fx, m[5], fyb, m[8]);
+            X = make_float2(dot2(m[0], fx, m[3], fya, m[6]) / wa, dot2(m[0], fx, m[3], fyb, m[6]) / wb);
+            Y = make_float2(dot2(m[1], fx, m[4], fya, m[7]) / wa, dot2(m[1], fx, m[4], fyb, m[7]) / wb);
+            Z = make_float2(a.z, a.z);
+        }
+        slots[((h >> 8) & 0xff) * 32] = X;
+        slots[((h >> 16) & 0xff) * 32] = Y;
+        slots[(h >> 24) * 32] = Z;
+
+        int pos = tile.tape;
+        unsigned cells = 0;
+        uint64_t d_next = arena[pos + 1];
+        uint64_t d;
+        for (;;) {
+            ++pos;
+            d = d_next;
+            const uint32_t w = uint32_t(d);
+            const uint32_t op = w & 0xff;
+            if (op == OP_END) break;
+            ++cells;
+            if (op == OP_JUMP) {
+                pos += int32_t(d >> 32);
+                d_next = arena[pos + 1];
+                continue;
+            }
+            d_next = arena[pos + 1];
+            const uint32_t i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
+            const float imm = __uint_as_float(uint32_t(d >> 32));
+            const float2 L = slots[i_lhs * 32];
+            const float2 R = slots[i_rhs * 32];
+            float2 o;
+            switch (op) {   // context.cu:887-920; no a*b+c shapes here, so nothing contracts
+                case OP_SQUARE: o = make_float2(__fmul_rn(L.x, L.x), __fmul_rn(L.y, L.y)); break;
+                case OP_SQRT:   o = make_float2(sqrtf(L.x), sqrtf(L.y)); break;
+                case OP_NEG:    o = make_float2(-L.x, -L.y); break;
+                case OP_SIN:    o = make_float2(sinf(L.x), sinf(L.y)); break;
+                case OP_COS:    o = make_float2(cosf(L.x), cosf(L.y)); break;
+                case OP_ASIN:   o = make_float2(asinf(L.x), asinf(L.y)); break;
+                case OP_ACOS:   o = make_float2(acosf(L.x), acosf(L.y)); break;
+                case OP_ATAN:   o = make_float2(atanf(L.x), atanf(L.y)); break;
+                case OP_EXP:    o = make_float2(expf(L.x), expf(L.y)); break;
+                case OP_ABS:    o = make_float2(fabsf(L.x), fabsf(L.y)); break;
+                case OP_LOG:    o = make_float2(logf(L.x), logf(L.y)); break;
+                case OP_ADD_LI: o = make_float2(__fadd_rn(L.x, imm), __fadd_rn(L.y, imm)); break;
+                case OP_ADD_LR: o = make_float2(__fadd_rn(L.x, R.x), __fadd_rn(L.y, R.y)); break;
+                case OP_MUL_LI: o = make_float2(__fmul_rn(L.x, imm), __fmul_rn(L.y, imm)); break;
+                case OP_MUL_LR: o = make_float2(__fmul_rn(L.x, R.x), __fmul_rn(L.y, R.y)); break;
+                case OP_MIN_LI: o = make_float2(fminf(L.x, imm), fminf(L.y, imm)); break;
+                case OP_MIN_LR: o = make_float2(fminf(L.x, R.x), fminf(L.y, R.y)); break;
+                case OP_MAX_LI: o = make_float2(fmaxf(L.x, imm), fmaxf(L.y, imm)); break;
+                case OP_MAX_LR: o = make_float2(fmaxf(L.x, R.x), fmaxf(L.y, R.y)); break;
+                case OP_SUB_LI: o = make_float2(__fsub_rn(L.x, imm), __fsub_rn(L.y, imm)); break;
+                case OP_SUB_IR: o = make_float2(__fsub_rn(imm, R.x), __fsub_rn(imm, R.y)); break;
+                case OP_SUB_LR: o = make_float2(__fsub_rn(L.x, R.x), __fsub_rn(L.y, R.y)); break;
+                case OP_DIV_LI: o = make_float2(__fdiv_rn(L.x, imm), __fdiv_rn(L.y, imm)); break;
+                case OP_DIV_IR: o = make_float2(__fdiv_rn(imm, R.x), __fdiv_rn(imm, R.y)); break;
+                case OP_DIV_LR: o = make_float2(__fdiv_rn(L.x, R.x), __fdiv_rn(L.y, R.y)); break;
+                case OP_COPY_IMM: o = make_float2(imm, imm); break;
+                case OP_COPY_LHS: o = L; break;
+                case OP_COPY_RHS: o = R; break;
+                default: o = L; break;
+            }
+            slots[i_out * 32] = o;
+        }
+        const float2 r = slots[((uint32_t(d) >> 8) & 0xff) * 32];
+        if (alive) {
+            if (DIM == 3) {
+                // The second sample is higher, so it wins when both are inside (context.cu:936-948)
+                if (r.y < 0.0f) atomicMax(&a.image[img_b], pz + 2);
+                else if (r.x < 0.0f) atomicMax(&a.image[img_a], pz);
+            } else {
+                if (r.y < 0.0f) a.image[img_b] = 1;
+                if (r.x < 0.0f) a.image[img_a] = 1;
+            }
+        }
+        if (lane == 0) {
+            atomicAdd(&a.ctl->stats[ST_F_TILES], 1ull);
+            atomicAdd(&a.ctl->stats[ST_F_CELLS], (unsigned long long)cells);
+        }
+    }
+}
+
+////////////////////////////////////////////////////////////////////////////////
+// Normal pass (eval_pixels_d, context.cu:978-1132)
+
+__global__ void __launch_bounds__(kEvalThreads)
+k_normals(const NormalsArgs a, const Mat4 mat)
+{
+    extern __shared__ float4 s_dslots[];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    float4* const slots = s_dslots + size_t(warp) * a.n_slots * 32 + lane;
+    const uint64_t* const arena = a.arena;
+    const uint32_t h = uint32_t(arena[0]);
+    const int size = a.size;
+    const int blocks_x = size / 8;              // a warp owns an 8 x 4 pixel block
+    const int n_items = blocks_x * ((a.y_end - a.y_begin) / 4);
+
+    for (;;) {
+        const int item = warp_next(a.queue);
+        if (item >= n_items) break;
+        const int px = (item % blocks_x) * 8 + (lane & 7);
+        const int py = a.y_begin + (item / blocks_x) * 4 + (lane >> 3);
+        const int pxy = px + py * size;
+        int pz = a.image[pxy];
+        int tape = -1;
+        if (pz != 0) {
+            // Step just in front of the surface unless that leaves the volume (context.cu:997-1005)
+            if (pz < size - 1) pz += 1;
+            // Deepest tile that contains this voxel (context.cu:1034-1066)
+            const int t0n = size / 64;
+            const int t0 = px / 64 + (py / 64) * t0n + (pz / 64) * t0n * t0n;
+            const TileNode n0 = a.tiles0[t0];
+            if (n0.next == -1) {
+                tape = n0.tape;
+            } else {
+                const int t1 = n0.next * 64 + (px % 64) / 16 + ((py % 64) / 16) * 4 + ((pz % 64) / 16) * 16;
+                const TileNode n1 = a.tiles1[t1];
+                if (n1.next == -1) {
+                    tape = n1.tape;
+                } else {
+                    const int t2 = n1.next * 64 + (px % 16) / 4 + ((py % 16) / 4) * 4 + ((pz % 16) / 4) * 16;
+                    tape = a.tiles2[t2].tape;
+                }
+            }
+        }
+        unsigned todo = __ballot_sync(kFull, tape >= 0);
+        if (!todo) continue;
+
+        // Sample position and seed gradients (context.cu:1009-1029)
+        dval sx_, sy_, sz_;
+        {
+            const float recip = 1.0f / float(size);
+            const float fx = sample_coord(px, recip), fy = sample_coord(py, recip);
+            const float fz = sample_coord(pz, recip);
+            const float* m = mat.d;
+            const float w = dot3(m[3], fx, m[7], fy, m[11], fz, m[15]);
+            sx_ = dv(dot3(m[0], fx, m[4], fy, m[8], fz, m[12]) / w, 1.0f, 0.0f, 0.0f);
+            sy_ = dv(dot3(m[1], fx, m[5], fy, m[9], fz, m[13]) / w, 0.0f, 1.0f, 0.0f);
+            sz_ = dv(dot3(m[2], fx, m[6], fy, m[10], fz, m[14]) / w, 0.0f, 0.0f, 1.0f);
+        }
+
+        dval result = dv_const(0.0f);
+        unsigned my_cells = 0;
+        // Lanes that share a tape walk it together; distinct tapes take turns.
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const int cur = __shfl_sync(kFull, tape, leader);
+            const bool mine = (tape == cur);
+            todo &= ~__ballot_sync(kFull, mine);
+
+            // The reference binds x, then y, then z, and then overwrites the
+            // gradient components through the same slot indices; with distinct
+            // slots that is exactly these three stores.  (An unused axis maps
+            // to slot 0, which no clause reads.)
+            slots[((h >> 8) & 0xff) * 32] = sx_;
+            slots[((h >> 16) & 0xff) * 32] = sy_;
+            slots[(h >> 24) * 32] = sz_;
+
+            int pos = cur;
+            unsigned cells = 0;
+            uint64_t d_next = arena[pos + 1];
+            uint64_t d;
+            for (;;) {
+                ++pos;
+                d = d_next;
+                const uint32_t w = uint32_t(d);
+                const uint32_t op = w & 0xff;
+                if (op == OP_END) break;
+                ++cells;
+                if (op == OP_JUMP) {
+                    pos += int32_t(d >> 32);
+                    d_next = arena[pos + 1];
+                    continue;
+                }
+                d_next = arena[pos + 1];
+                const uint32_t i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
+                const float imm = __uint_as_float(uint32_t(d >> 32));
+                const dval L = slots[i_lhs * 32];
+                const dval R = slots[i_rhs * 32];
+                dval o;
+                switch (op) {   // context.cu:1081-1114
+                    case OP_SQUARE: o = dv_mul(L, L); break;
+                    case OP_SQRT:   o = dv_sqrt(L); break;
+                    case OP_NEG:    o = dv_neg(L); break;
+                    case OP_SIN:    o = dv_sin(L); break;
+                    case OP_COS:    o = dv_cos(L); break;
+                    case OP_ASIN:   o = dv_asin(L); break;
+                    case OP_ACOS:   o = dv_acos(L); break;
+                    case OP_ATAN:   o = dv_atan(L); break;
+                    case OP_EXP:    o = dv_exp(L); break;
+                    case OP_ABS:    o = dv_abs(L); break;
+                    case OP_LOG:    o = dv_log(L); break;
+                    case OP_ADD_LI: o = dv_add(L, imm); break;
+                    case OP_ADD_LR: o = dv_add(L, R); break;
+                    case OP_MUL_LI: o = dv_mul(L, imm); break;
+                    case OP_MUL_LR: o = dv_mul(L, R); break;
+                    case OP_MIN_LI: o = dv_min(L, imm); break;
+                    case OP_MIN_LR: o = dv_min(L, R); break;
+                    case OP_MAX_LI: o = dv_max(L, imm); break;
+                    case OP_MAX_LR: o = dv_max(L, R); break;
+                    case OP_SUB_LI: o = dv_sub(L, imm); break;
+                    case OP_SUB_IR: o = dv_sub(imm, R); break;
+                    case OP_SUB_LR: o = dv_sub(L, R); break;
+                    case OP_DIV_LI: o = dv_div(L, imm); break;
+                    case OP_DIV_IR: o = dv_div(imm, R); break;
+                    case OP_DIV_LR: o = dv_div(L, R); break;
+                    case OP_COPY_IMM: o = dv_const(imm); break;
+                    case OP_COPY_LHS: o = L; break;
+                    case OP_COPY_RHS: o = R; break;
+                    default: o = L; break;
+                }
+                slots[i_out * 32] = o;
+            }
+            if (mine) {
+                result = slots[((uint32_t(d) >> 8) & 0xff) * 32];
+                my_cells = cells;
+            }
+        }
+
+        if (tape >= 0) {
+            // context.cu:1123-1131 (SASS: powf x3, FADD, FADD, sqrt; div; FFMA 127,128; F2I.U32.TRUNC)
+            const float norm = sqrtf(__fadd_rn(__fadd_rn(powf(result.x, 2), powf(result.y, 2)),
+                                               powf(result.z, 2)));
+            const uint8_t bx = __fmaf_rn(__fdiv_rn(result.x, norm), 127.0f, 128.0f);
+            const uint8_t by = __fmaf_rn(__fdiv_rn(result.y, norm), 127.0f, 128.0f);
+            const uint8_t bz = __fmaf_rn(__fdiv_rn(result.z, norm), 127.0f, 128.0f);
+            a.normals[pxy] = (0xFFu << 24) | (uint32_t(bz) << 16) | (uint32_t(by) << 8) | bx;
+        }
+        {
+            const unsigned n_px = __popc(__ballot_sync(kFull, tape >= 0));
+            const unsigned long long c_sum = warp_sum(tape >= 0 ? my_cells : 0u);
+            if (lane == 0) {
+                atomicAdd(&a.ctl->stats[ST_N_PIXELS], (unsigned long long)n_px);
+                atomicAdd(&a.ctl->stats[ST_N_CELLS], c_sum);
+            }
+        }
+    }
+}
+
+////////////////////////////////////////////////////////////////////////////////
+// Frame setup: clear the control block and set the arena allocation cursor.
+
+__global__ void k_begin_frame(FrameCtl* ctl, int32_t first_free)
+{
+    const int i = threadIdx.x;
+    int32_t* raw = reinterpret_cast<int32_t*>(ctl);
+    for (int k = i; k < int(sizeof(FrameCtl) / 4); k += blockDim.x) raw[k] = 0;
+    __syncthreads();
+    if (i == 0) ctl->tape_cursor = first_free;
+}
+
+////////////////////////////////////////////////////////////////////////////////
+// Launch wrappers
+
+// Opt every kernel in to the device's full dynamic shared memory once.
+void init_kernels(int max_smem_optin) {
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    cudaFuncSetAttribute(k_eval_tiles<2, true>, attr, max_smem_optin);
+    cudaFuncSetAttribute(k_eval_tiles<2, false>, attr, max_smem_optin);
+    cudaFuncSetAttribute(k_eval_tiles<3, true>, attr, max_smem_optin);
+    cudaFuncSetAttribute(k_eval_tiles<3, false>, attr, max_smem_optin);
+    cudaFuncSetAttribute(k_eval_voxels<2>, attr, max_smem_optin);
+    cudaFuncSetAttribute(k_eval_voxels<3>, attr, max_smem_optin);
+    cudaFuncSetAttribute(k_normals, attr, max_smem_optin);
+}
+
+template <int DIM, bool ROOT>
+static void launch_eval_tiles_t(const EvalTilesArgs& a, const void* mat, int grid, cudaStream_t s) {
+    const size_t smem = size_t(kEvalWarps) * a.n_slots * 32 * sizeof(float2);
+    auto kernel = k_eval_tiles<DIM, ROOT>;
+    kernel<<<grid, kEvalThreads, smem, s>>>(a, *static_cast<const typename MatOf<DIM>::type*>(mat));
+}
+
+void launch_eval_tiles(int dim, bool root, const EvalTilesArgs& a, const void* mat, int grid, cudaStream_t s) {
+    if (dim == 3) {
+        if (root) launch_eval_tiles_t<3, true>(a, mat, grid, s);
+        else launch_eval_tiles_t<3, false>(a, mat, grid, s);
+    } else {
+        if (root) launch_eval_tiles_t<2, true>(a, mat, grid, s);
+        else launch_eval_tiles_t<2, false>(a, mat, grid, s);
+    }
+}
+
+void launch_rank_tiles(int dim, const RankArgs& a, int grid, cudaStream_t s) {
+    if (dim == 3) k_rank_tiles<3><<<grid, 256, 0, s>>>(a);
+    else k_rank_tiles<2><<<grid, 256, 0, s>>>(a);
+}
+
+void launch_upsample_filled(int dim, const int32_t* prev, int32_t* image, int size, int grid, cudaStream_t s) {
+    if (dim == 3) k_upsample_filled<3><<<grid, 256, 0, s>>>(prev, image, size);
+    else k_upsample_filled<2><<<grid, 256, 0, s>>>(prev, image, size);
+}
+
+void launch_eval_voxels(int dim, const EvalVoxelsArgs& a, const void* mat, int grid, cudaStream_t s) {
+    const size_t smem = size_t(kEvalWarps) * a.n_slots * 32 * sizeof(float2);
+    if (dim == 3) {
+        k_eval_voxels<3><<<grid, kEvalThreads, smem, s>>>(a, *static_cast<const Mat4*>(mat));
+    } else {
+        k_eval_voxels<2><<<grid, kEvalThreads, smem, s>>>(a, *static_cast<const Mat3*>(mat));
+    }
+}
+
+void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
+    const size_t smem = size_t(kEvalWarps) * a.n_slots * 32 * sizeof(float4);
+    k_normals<<<grid, kEvalThreads, smem, s>>>(a, mat);
+}
+
+void launch_begin_frame(FrameCtl* ctl, int32_t first_free, cudaStream_t s) {
+    k_begin_frame<<<1, 64, 0, s>>>(ctl, first_free);
+}
+
+int occupancy_eval_tiles(int dim, bool root, int n_slots) {
+    const size_t smem = size_t(kEvalWarps) * n_slots * 32 * sizeof(float2);
+    int n = 0;
+    if (dim == 3) {
+        if (root) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_tiles<3, true>, kEvalThreads, smem); }
+        else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_tiles<3, false>, kEvalThreads, smem); }
+    } else {
+        if (root) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_tiles<2, true>, kEvalThreads, smem); }
+        else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_tiles<2, false>, kEvalThreads, smem); }
+    }
+    return n;
+}
+
+int occupancy_eval_voxels(int dim, int n_slots) {
+    const size_t smem = size_t(kEvalWarps) * n_slots * 32 * sizeof(float2);
+    int n = 0;
+    if (dim == 3) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_voxels<3>, kEvalThreads, smem); }
+    else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_voxels<2>, kEvalThreads, smem); }
+    return n;
+}
+
+int occupancy_normals(int n_slots) {
+    const size_t smem = size_t(kEvalWarps) * n_slots * 32 * sizeof(float4);
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_normals, kEvalThreads, smem);
+    return n;
+}
+
+}  // namespace mprb

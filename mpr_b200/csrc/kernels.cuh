@@ -1,0 +1,92 @@
+// Kernel argument blocks and host-callable launchers (see kernels.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace mprb {
+
+constexpr int kEvalWarps = 4;                 // warps per CTA in the tape-walking kernels
+constexpr int kEvalThreads = kEvalWarps * 32;
+
+struct EvalTilesArgs {
+    uint64_t* arena;          // tape arena; root tape at cell 0
+    int32_t* tape_index;      // arena allocation cursor (cells)
+    int32_t arena_cap;        // arena size in cells
+    int32_t* image;           // this level's filled image, tps x tps
+    TileNode* tiles;          // this level's tile records (written)
+    int32_t tiles_cap;        // capacity of `tiles`
+    uint32_t tps;             // tiles per side at this level
+    const TileNode* ptiles;   // parent level (null at the root)
+    const int32_t* pactive;   // parent rank -> index into ptiles
+    const int32_t* n_parents; // device count of active parents
+    uint32_t ptps;            // parent tiles per side
+    int32_t count0;           // root level: number of tiles
+    int32_t row_begin;        // root level: this context renders tile rows
+    int32_t row_end;          //   [row_begin, row_end) in y (multi-GPU sharding)
+    FrameCtl* ctl;
+    int32_t* queue;           // work-queue head for this launch
+    int32_t level;            // 0, 1, 2 (statistics slot / overflow bit)
+    int32_t n_slots;          // slot ids used by the root tape, +1
+    float z;                  // 2D only: the constant z
+};
+
+struct RankArgs {
+    TileNode* tiles;          // this level's tile records
+    int32_t tiles_cap;
+    const int32_t* n_parents; // null at the root level
+    int32_t count0;
+    int32_t tps;
+    const int32_t* image;     // this level's filled image
+    int32_t* n_active;        // out: survivors
+    int32_t* active_list;     // out: rank -> tile index (not at the last level)
+    TileNode* out_tiles;      // out: compact survivor list (last level only)
+    long long next_cap;       // capacity (tiles) of the stage that receives survivors
+    int32_t last_level;
+    int32_t level;
+    FrameCtl* ctl;
+};
+
+struct EvalVoxelsArgs {
+    const uint64_t* arena;
+    int32_t* image;           // full-resolution image / heightmap
+    const TileNode* tiles;    // compact survivor list of the last interval level
+    int32_t tiles_cap;
+    const int32_t* n_tiles;
+    uint32_t tps;             // survivor-level tiles per side (size/4 or size/8)
+    FrameCtl* ctl;
+    int32_t* queue;
+    int32_t n_slots;
+    float z;
+};
+
+struct NormalsArgs {
+    const uint64_t* arena;
+    const int32_t* image;     // heightmap
+    uint32_t* normals;
+    int32_t size;
+    int32_t y_begin;          // pixel rows [y_begin, y_end) belong to this context
+    int32_t y_end;
+    const TileNode* tiles0;
+    const TileNode* tiles1;
+    const TileNode* tiles2;
+    FrameCtl* ctl;
+    int32_t* queue;
+    int32_t n_slots;
+};
+
+void init_kernels(int max_smem_optin);
+void launch_begin_frame(FrameCtl* ctl, int32_t first_free, cudaStream_t s);
+void launch_eval_tiles(int dim, bool root, const EvalTilesArgs& a, const void* mat, int grid, cudaStream_t s);
+void launch_rank_tiles(int dim, const RankArgs& a, int grid, cudaStream_t s);
+void launch_upsample_filled(int dim, const int32_t* prev, int32_t* image, int size, int grid, cudaStream_t s);
+void launch_eval_voxels(int dim, const EvalVoxelsArgs& a, const void* mat, int grid, cudaStream_t s);
+void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_t s);
+
+// Resident CTAs per SM for a given slot count (sizes the persistent grids).
+int occupancy_eval_tiles(int dim, bool root, int n_slots);
+int occupancy_eval_voxels(int dim, int n_slots);
+int occupancy_normals(int n_slots);
+
+}  // namespace mprb

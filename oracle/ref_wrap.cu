@@ -1,0 +1,78 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product path.
+//
+// A C-ABI shim around the UNMODIFIED reference renderer so that tests and the
+// bench's reference arm can drive it with ctypes.  It is compiled together
+// with the reference's own sources *where they lie* under /root/reference
+// (src/context.cu, src/context.cpp, src/gpu_opcode.cu + inc/*.hpp) by
+// oracle/Makefile into oracle/_ref/libmpr_ref.so; no reference source is
+// copied into this repository.
+//
+// The reference builds mpr::Tape from a libfive::Tree (src/tape.cpp), and
+// libfive cannot be built here (Eigen/Boost/libpng are absent).  tape.hpp only
+// forward-declares libfive::Tree, so this file supplies a carrier type with
+// that name which simply holds an already-packed clause array, plus the
+// Tape constructor that uploads it the way src/tape.cpp:223-227 does.
+#include <cstdint>
+#include <cstring>
+
+#include "context.hpp"
+#include "parameters.hpp"
+#include "tape.hpp"
+
+namespace libfive {
+class Tree {
+public:
+    const uint64_t* cells;
+    int32_t n;
+};
+}  // namespace libfive
+
+namespace mpr {
+Tape::Tape(const libfive::Tree& t) {
+    data.reset(CUDA_MALLOC(uint64_t, t.n));
+    CUDA_CHECK(cudaMemcpy(data.get(), t.cells, sizeof(uint64_t) * t.n,
+                          cudaMemcpyHostToDevice));
+    length = t.n;
+}
+}  // namespace mpr
+
+extern "C" {
+
+void* ref_ctx_create(int image_size_px) { return new mpr::Context(image_size_px); }
+void ref_ctx_destroy(void* c) { delete static_cast<mpr::Context*>(c); }
+
+void* ref_tape_create(const uint64_t* host_cells, int32_t n) {
+    libfive::Tree t;
+    t.cells = host_cells;
+    t.n = n;
+    return new mpr::Tape(t);
+}
+void ref_tape_destroy(void* t) { delete static_cast<mpr::Tape*>(t); }
+
+void ref_render2d(void* c, void* t, const float* mat3_colmajor, float z) {
+    Eigen::Matrix3f m;
+    memcpy(m.d, mat3_colmajor, sizeof(float) * 9);
+    static_cast<mpr::Context*>(c)->render2D(*static_cast<mpr::Tape*>(t), m, z);
+}
+void ref_render3d(void* c, void* t, const float* mat4_colmajor) {
+    Eigen::Matrix4f m;
+    memcpy(m.d, mat4_colmajor, sizeof(float) * 16);
+    static_cast<mpr::Context*>(c)->render3D(*static_cast<mpr::Tape*>(t), m);
+}
+
+int32_t* ref_filled(void* c, int stage) {
+    return static_cast<mpr::Context*>(c)->stages[stage].filled.get();
+}
+void* ref_tiles(void* c, int stage) {
+    return static_cast<mpr::Context*>(c)->stages[stage].tiles.get();
+}
+uint64_t ref_tile_array_size(void* c, int stage) {
+    return static_cast<mpr::Context*>(c)->stages[stage].tile_array_size;
+}
+uint64_t* ref_tape_data(void* c) { return static_cast<mpr::Context*>(c)->tape_data.get(); }
+int32_t ref_tape_index(void* c) { return *static_cast<mpr::Context*>(c)->tape_index; }
+int32_t ref_num_active(void* c) { return *static_cast<mpr::Context*>(c)->num_active_tiles; }
+uint32_t* ref_normals(void* c) { return static_cast<mpr::Context*>(c)->normals.get(); }
+int64_t ref_num_subtapes(void) { return NUM_SUBTAPES; }
+
+}  // extern "C"
