@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: ms/frame of the tile-recursive renderer on the reference's
+own benchmark models (BASELINE.json: "ms/frame at 256-4096 on prospero 2D + bear 3D;
+eval_tiles_i HBM GB/s vs peak").
+
+A *step* renders one frame of every workload in --workload (default: the two headline
+configurations of BASELINE.json's north_star, prospero 2D 4096x4096 and bear 3D 1024^3);
+`value` is the mean ms per frame.  The protocol follows the reference's table drivers
+(benchmark/render_2d_table.cpp, render_3d_table.cpp, stats.cpp): context built outside the
+timed region, identity view in 2D, T(3,2)=0.3 perspective in 3D, frame time includes the
+final device synchronisation.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          this repository's CUDA path
+  python bench.py --impl reference ...                         the UNMODIFIED reference CUDA
+                                                               renderer (oracle/_ref), same workload
+Both arms also time the CPU restatement (oracle/) on the host cores as `cpu_baseline`.
+Under torchrun (N > 1) every rank renders a band of 64-px tile rows and the bands are
+exchanged with one NCCL all-gather per frame.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "ms/frame (prospero 2D + bear 3D)"
+SUBTAPES = 6400000          # arena chunks: the reference's BIG_SERVER setting, both arms
+PEAKS = ROOT / "MEASURED_PEAKS.json"
+HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_workloads(spec: str):
+    out = []
+    for w in spec.split(","):
+        model, dim, size = w.rsplit("_", 2)
+        out.append((model, int(dim[0]), int(size)))
+    return out
+
+
+def load_tape(model: str) -> np.ndarray:
+    return np.fromfile(ROOT / "tests" / "golden" / "tapes" / f"{model}.u64", dtype="<u8")
+
+
+class ClockSampler:
+    """nvidia-smi samples while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(workloads, budget_s: float = 60.0) -> dict:
+    """The CPU restatement (oracle/mpr_oracle.c) on all host cores: one frame per workload."""
+    import oracle
+    t_total, frames, sample = 0.0, 0, []
+    threads = oracle.oracle_lib().mpro_max_threads()
+    for model, dim, size in workloads:
+        if t_total > budget_s:
+            break
+        o = oracle.CpuOracle(size, SUBTAPES)
+        cells = load_tape(model)
+        t0 = time.perf_counter()
+        (o.render2D if dim == 2 else o.render3D)(cells, threads=threads)
+        dt = time.perf_counter() - t0
+        o.close()
+        t_total += dt
+        frames += 1
+        sample.append(f"{model}_{dim}d_{size}: {dt * 1e3:.1f} ms")
+    return {"value": t_total * 1e3 / max(frames, 1), "unit": "ms/frame", "cores": threads, "kind": "port",
+            "sample": "one frame of each workload, oracle/mpr_oracle.c with OpenMP over tiles (" + "; ".join(sample) + ")"}
+
+
+# Launch order inside one frame (mpr_b200/csrc/api.cu: render()).
+KERNELS_2D = ["eval_tiles", "rank_tiles", "upsample_filled"] * 2 + ["eval_voxels"]
+KERNELS_3D = ["eval_tiles", "rank_tiles", "upsample_filled"] * 3 + ["eval_voxels", "normals"]
+
+
+def algorithmic_bytes(st, kernel: str) -> float:
+    """Bytes a kernel must move per frame by the per-tile formulas of SURVEY.md section 8(d)
+    (tape counted once per tile evaluation).  st = mprb_frame_stats of that frame."""
+    if kernel == "eval_tiles":
+        b = 0.0
+        for l in range(3):
+            # TileNode 12 + values 24 (+4 image) + 8*(F+1) read, 4 written; pushes re-read the tape
+            # and write 8 bytes per kept cell (clauses, header, end cell, chunk links) + tile.tape
+            b += st.i_tiles[l] * (12 + 24 + 4 + 8 + 4) + 8.0 * st.i_cells[l]
+            b += 8.0 * st.p_cells[l] + 8.0 * st.p_kept[l] + 4.0 * st.p_tiles[l]
+        return b
+    if kernel == "eval_voxels":
+        return st.f_tiles * (12 + 768 + 8 + 256) + 8.0 * st.f_cells
+    if kernel == "normals":
+        return st.n_pixels * (36 + 4 + 8 + 4) + 8.0 * st.n_cells
+    return 0.0
+
+
+def run_mine(args, workloads):
+    import torch
+    import torch.distributed as dist
+    from mpr_b200 import capi, sharding
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    class DevArray:   # wraps a raw device pointer for torch.as_tensor
+        def __init__(self, ptr, n, typestr):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+    jobs = []
+    for model, dim, size in workloads:
+        b, e = sharding.band_rows(size, world, rank)
+        ctx = capi.Context(size, device=local, num_subtapes=SUBTAPES, row_begin=b, row_end=e)
+        cells_pinned = torch.from_numpy(load_tape(model).view(np.int64).copy()).pin_memory()
+        cells = cells_pinned.numpy().view(np.uint64)
+        tape = capi.Tape(cells)
+        out_img = torch.empty((size, size), dtype=torch.int32).pin_memory()
+        out_nrm = torch.empty((size, size), dtype=torch.int32).pin_memory() if dim == 3 else None
+        job = dict(model=model, dim=dim, size=size, ctx=ctx, tape=tape, cells=cells, keep=cells_pinned,
+                   out_img=out_img, out_nrm=out_nrm, sl=sharding.band_slice(size, world, rank))
+        if world > 1:
+            ptr, nbytes = ctx.device_image()
+            job["dev_img"] = torch.as_tensor(DevArray(ptr, size * size, "<i4"), device=f"cuda:{local}").view(size, size)
+            job["gather"] = torch.empty((size, size), dtype=torch.int32, device=f"cuda:{local}")
+            if dim == 3:
+                ptr, nbytes = ctx.device_normals()
+                job["dev_nrm"] = torch.as_tensor(DevArray(ptr, size * size, "<i4"), device=f"cuda:{local}").view(size, size)
+                job["gather_n"] = torch.empty((size, size), dtype=torch.int32, device=f"cuda:{local}")
+        jobs.append(job)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
+
+    def gather(job):
+        """One all-gather of the band(s); returns device ms (0 on one GPU)."""
+        if world == 1:
+            return 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_gather_into_tensor(job["gather"].view(-1), job["dev_img"][job["sl"]].reshape(-1))
+        job["dev_img"].copy_(job["gather"])       # every rank ends up holding the full frame
+        if job["dim"] == 3:
+            dist.all_gather_into_tensor(job["gather_n"].view(-1), job["dev_nrm"][job["sl"]].reshape(-1))
+            job["dev_nrm"].copy_(job["gather_n"])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    def frame_device(job):
+        ctx = job["ctx"]
+        (ctx.render2D if job["dim"] == 2 else ctx.render3D)(job["tape"])
+        ms = ctx.stats().gpu_ms
+        return ms + gather(job)
+
+    def frame_e2e(job):
+        ctx = job["ctx"]
+        t0 = time.perf_counter()
+        if world == 1:
+            if job["dim"] == 2:
+                ctx.render2D_host(job["cells"], job["out_img"].numpy())
+            else:
+                ctx.render3D_host(job["cells"], job["out_img"].numpy(), job["out_nrm"].numpy().view(np.uint32))
+        else:
+            if job["dim"] == 2:
+                ctx.render2D_host(job["cells"], None)
+            else:
+                ctx.render3D_host(job["cells"], None, None)
+            gather(job)
+            job["out_img"].copy_(job["dev_img"])
+            if job["dim"] == 3:
+                job["out_nrm"].copy_(job["dev_nrm"])
+            torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(fn):
+        flush.zero_()             # evict L2 between steps (outside every timed window)
+        barrier()
+        return [fn(j) for j in jobs]
+
+    for _ in range(args.warmup):
+        step(frame_device)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    dev = np.array([step(frame_device) for _ in range(args.steps)])      # [K, n_jobs] device ms
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = sum(j["ctx"].stats().n_launches for j in jobs)
+    for _ in range(min(args.warmup, 3)):
+        step(frame_e2e)
+    e2e = np.array([step(frame_e2e) for _ in range(args.steps)])         # [K, n_jobs] wall ms
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+
+    # per-kernel timing + counters on separate frames (events between launches perturb nothing
+    # in the timed loops above)
+    per_kernel, bytes_by_kernel, frames_k = {}, {}, 3
+    stats_one = {}
+    for j in jobs:
+        ctx = j["ctx"]
+        ctx.set_timing(True)
+        names = KERNELS_2D if j["dim"] == 2 else KERNELS_3D
+        for _ in range(frames_k):
+            flush.zero_()
+            torch.cuda.synchronize()
+            (ctx.render2D if j["dim"] == 2 else ctx.render3D)(j["tape"])
+            st = ctx.stats()
+            for name, ms in zip(names, list(st.kernel_ms)[: st.n_launches]):
+                per_kernel[name] = per_kernel.get(name, 0.0) + ms / frames_k
+            for name in set(names):
+                bytes_by_kernel[name] = bytes_by_kernel.get(name, 0.0) + algorithmic_bytes(st, name) / frames_k
+        ctx.set_timing(False)
+        st = ctx.stats()
+        stats_one[f"{j['model']}_{j['dim']}d_{j['size']}"] = {
+            "n_active": list(st.n_active), "tape_index": st.tape_index, "interval_tiles": list(st.i_tiles),
+            "interval_cells": list(st.i_cells), "float_tiles": st.f_tiles, "float_cells": st.f_cells}
+
+    # max over ranks, step by step
+    if world > 1:
+        t = torch.tensor(np.concatenate([dev.sum(1), e2e.sum(1)]), device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = t.cpu().numpy()
+        dev_step, e2e_step = t[: args.steps], t[args.steps:]
+    else:
+        dev_step, e2e_step = dev.sum(1), e2e.sum(1)
+
+    if rank == 0:
+        n_frames = len(jobs)
+        peak = json.loads(PEAKS.read_text())["hbm_gbs"] if PEAKS.exists() else HBM_FALLBACK_GBS
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (copy, burst)" if PEAKS.exists() else "B200_PROFILING.md fallback"
+        dom = max((k for k in per_kernel if bytes_by_kernel.get(k, 0) > 0), key=lambda k: per_kernel[k])
+
+        def roof(k):
+            ach = bytes_by_kernel[k] / (per_kernel[k] * 1e-3) / 1e9 if per_kernel[k] > 0 else 0.0
+            return {"kernel": "k_" + k, "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 5), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_step": int(bytes_by_kernel[k]), "kernel_ms_per_step": round(per_kernel[k], 4)}
+
+        h2d = sum(j["cells"].nbytes + (64 if j["dim"] == 3 else 36) for j in jobs)
+        d2h = sum(j["size"] ** 2 * 4 * (2 if j["dim"] == 3 else 1) for j in jobs)
+        line = {
+            "metric": METRIC, "value": float(dev_step.mean() / n_frames), "unit": "ms/frame",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(dev_step.mean()), "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "the reference's benchmark models as packed tapes (tests/golden/tapes)",
+            "config": {"workload": "+".join(f"{j['model']}_{j['dim']}d_{j['size']}" for j in jobs),
+                       "frames_per_step": n_frames, "view": "2D identity, 3D T(3,2)=0.3 (reference table drivers)",
+                       "parallelism": f"tile-row bands x{world}" + (", 1 NCCL all-gather/frame" if world > 1 else ""),
+                       "num_subtapes": SUBTAPES, "l2": "flushed between steps (256 MiB memset, untimed)",
+                       "timing": "CUDA events on the render stream per frame (+ all-gather events), max over ranks",
+                       "ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(dev[:, i].mean()) for i, j in enumerate(jobs)},
+                       "e2e_ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(e2e[:, i].mean()) for i, j in enumerate(jobs)},
+                       "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
+                       "frame_stats": stats_one},
+            "clocks": clk,
+            "e2e": {"value": float(e2e_step.mean() / n_frames), "unit": "ms/frame", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "kernel_ms_per_step": {k: round(v, 4) for k, v in per_kernel.items()},
+            "roofline": roof(dom),
+            "roofline_eval_tiles": roof("eval_tiles"),
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(workloads)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args, workloads):
+    """The unmodified reference CUDA renderer (single GPU, default stream, managed memory)."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import oracle
+    if not oracle.ref_available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmpr_ref.so missing (build needs /root/reference)"}))
+        return
+    jobs = []
+    for model, dim, size in workloads:
+        ref = oracle.RefGpu(size)
+        cells = load_tape(model)
+        jobs.append(dict(model=model, dim=dim, size=size, ref=ref, cells=cells,
+                         img=np.zeros((size, size), dtype=np.int32),
+                         nrm=np.zeros((size, size), dtype=np.uint32) if dim == 3 else None))
+
+    def frame(job):     # the reference's own protocol: wall clock around render*, which ends in a device sync
+        t0 = time.perf_counter()
+        (job["ref"].render2D if job["dim"] == 2 else job["ref"].render3D)(job["cells"])
+        return (time.perf_counter() - t0) * 1e3
+
+    def frame_e2e(job):  # + Tape construction from host cells, + download of the result
+        t0 = time.perf_counter()
+        job["ref"].drop_tapes()
+        (job["ref"].render2D if job["dim"] == 2 else job["ref"].render3D)(job["cells"])
+        job["ref"].download(job["img"], job["nrm"])
+        return (time.perf_counter() - t0) * 1e3
+
+    for _ in range(args.warmup):
+        [frame(j) for j in jobs]
+    clocks = ClockSampler(0)
+    clocks.start()
+    dev = np.array([[frame(j) for j in jobs] for _ in range(args.steps)])
+    for _ in range(min(args.warmup, 3)):
+        [frame_e2e(j) for j in jobs]
+    e2e = np.array([[frame_e2e(j) for j in jobs] for _ in range(args.steps)])
+    clk = clocks.stop()
+    n_frames = len(jobs)
+    h2d = sum(j["cells"].nbytes + (64 if j["dim"] == 3 else 36) for j in jobs)
+    d2h = sum(j["size"] ** 2 * 4 * (2 if j["dim"] == 3 else 1) for j in jobs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": float(dev.sum(1).mean() / n_frames), "unit": "ms/frame",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(dev.sum(1).mean()),
+        "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "the reference's benchmark models as packed tapes (tests/golden/tapes)",
+        "config": {"workload": "+".join(f"{j['model']}_{j['dim']}d_{j['size']}" for j in jobs), "frames_per_step": n_frames,
+                   "what": "unmodified reference src/context.cu + context.cpp + gpu_opcode.cu compiled for sm_100a with "
+                           "-DBIG_SERVER (oracle/Makefile), driven through oracle/ref_wrap.cu",
+                   "timing": "host wall clock around render2D/render3D incl. its cudaDeviceSynchronize (benchmark/stats.cpp protocol)",
+                   "ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(dev[:, i].mean()) for i, j in enumerate(jobs)},
+                   "e2e_ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(e2e[:, i].mean()) for i, j in enumerate(jobs)}},
+        "clocks": clk,
+        "e2e": {"value": float(e2e.sum(1).mean() / n_frames), "unit": "ms/frame", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h)},
+    }
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(workloads)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="mine", choices=["mine", "reference"])
+    ap.add_argument("--workload", default="prospero_2d_4096,bear_3d_1024")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    workloads = parse_workloads(args.workload)
+    if args.impl == "reference":
+        run_reference(args, workloads)
+    else:
+        run_mine(args, workloads)
+
+
+if __name__ == "__main__":
+    main()

@@ -104,7 +104,8 @@ int mprb_render3d(mprb_ctx* ctx, const mprb_tape* tape, const float mat4_colmajo
 
 /* Host-buffer variants: the tape cells come from (pinned or pageable) host
  * memory and the results are copied into host buffers before returning.
- * image_out: size*size int32; normals_out: size*size uint32 (may be NULL). */
+ * image_out / depth_out: size*size int32; normals_out: size*size uint32.  Any output pointer
+ * may be NULL to skip that download (multi-GPU callers gather bands on the device first). */
 int mprb_render2d_host(mprb_ctx* ctx, const uint64_t* host_cells, int32_t n_cells,
                        const float mat3_colmajor[9], float z, int32_t* image_out);
 int mprb_render3d_host(mprb_ctx* ctx, const uint64_t* host_cells, int32_t n_cells,

@@ -214,12 +214,14 @@ class Context:
     def render2D_host(self, cells: np.ndarray, image_out: np.ndarray, mat=None, z: float = 0.0):
         m = mat_colmajor(np.eye(3) if mat is None else mat)
         _check(lib().mprb_render2d_host(self._h, cells.ctypes.data, cells.size,
-                                        m.ctypes.data_as(C.POINTER(C.c_float)), z, image_out.ctypes.data))
+                                        m.ctypes.data_as(C.POINTER(C.c_float)), z,
+                                        image_out.ctypes.data if image_out is not None else None))
 
     def render3D_host(self, cells: np.ndarray, depth_out: np.ndarray, normals_out=None, mat=None):
         m = mat_colmajor(view_matrix_3d() if mat is None else mat)
         _check(lib().mprb_render3d_host(self._h, cells.ctypes.data, cells.size,
-                                        m.ctypes.data_as(C.POINTER(C.c_float)), depth_out.ctypes.data,
+                                        m.ctypes.data_as(C.POINTER(C.c_float)),
+                                        depth_out.ctypes.data if depth_out is not None else None,
                                         normals_out.ctypes.data if normals_out is not None else None))
 
     # -- buffer views (managed memory; valid until the next render call) ----------
@@ -256,6 +258,15 @@ class Context:
             return np.zeros(0, dtype=TILE_DTYPE)
         raw = np.ctypeslib.as_array(C.cast(b.tiles[stage], C.POINTER(C.c_int32)), shape=(n, 3))
         return raw.view(TILE_DTYPE).reshape(n)
+
+    def device_image(self):
+        """(ptr, nbytes) of stages[3].filled for wrapping as a device array."""
+        b = self.buffers()
+        return C.cast(b.filled[3], C.c_void_p).value, self.image_size_px * self.image_size_px * 4
+
+    def device_normals(self):
+        b = self.buffers()
+        return C.cast(b.normals, C.c_void_p).value, self.image_size_px * self.image_size_px * 4
 
     def tape_data(self, n_cells=None) -> np.ndarray:
         b = self.buffers()

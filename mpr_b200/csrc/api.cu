@@ -557,21 +557,23 @@ int mprb_render3d(mprb_ctx* c, const mprb_tape* t, const float mat4[16]) {
 
 int mprb_render2d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
                        const float mat3[9], float z, int32_t* image_out) {
-    if (!c || !mat3 || !image_out) return fail(MPRB_E_ARG, "null argument");
+    if (!c || !mat3) return fail(MPRB_E_ARG, "null argument");
     if (int e = validate_tape(host_cells, n_cells)) return e;
     if (int e = render(c, 2, host_cells, n_cells, true, tape_num_slots(host_cells, n_cells), mat3, z)) return e;
     const size_t n = size_t(c->size) * c->size;
-    MPRB_CUDA(cudaMemcpyAsync(image_out, c->filled[3], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (image_out)
+        MPRB_CUDA(cudaMemcpyAsync(image_out, c->filled[3], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
     return finish(c, 2);
 }
 
 int mprb_render3d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
                        const float mat4[16], int32_t* depth_out, uint32_t* normals_out) {
-    if (!c || !mat4 || !depth_out) return fail(MPRB_E_ARG, "null argument");
+    if (!c || !mat4) return fail(MPRB_E_ARG, "null argument");
     if (int e = validate_tape(host_cells, n_cells)) return e;
     if (int e = render(c, 3, host_cells, n_cells, true, tape_num_slots(host_cells, n_cells), mat4, 0.0f)) return e;
     const size_t n = size_t(c->size) * c->size;
-    MPRB_CUDA(cudaMemcpyAsync(depth_out, c->filled[3], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (depth_out)
+        MPRB_CUDA(cudaMemcpyAsync(depth_out, c->filled[3], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
     if (normals_out)
         MPRB_CUDA(cudaMemcpyAsync(normals_out, c->normals, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
     return finish(c, 3);

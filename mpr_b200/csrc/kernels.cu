@@ -833,15 +833,23 @@ __global__ void k_begin_frame(FrameCtl* ctl, int32_t first_free)
 // Launch wrappers
 
 // Opt every kernel in to the device's full dynamic shared memory once.
+// Also pin the L1/shared split to "all shared": occupancy here is bounded by shared memory,
+// and a device-wide cudaDeviceSetCacheConfig(PreferL1) made by other code in the process
+// (the reference's Context constructor does that, context.cpp:47-48) would otherwise shrink
+// the carve-out to one CTA per SM.
+template <typename K>
+static void opt_in(K kernel, int max_smem_optin) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 void init_kernels(int max_smem_optin) {
-    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    cudaFuncSetAttribute(k_eval_tiles<2, true>, attr, max_smem_optin);
-    cudaFuncSetAttribute(k_eval_tiles<2, false>, attr, max_smem_optin);
-    cudaFuncSetAttribute(k_eval_tiles<3, true>, attr, max_smem_optin);
-    cudaFuncSetAttribute(k_eval_tiles<3, false>, attr, max_smem_optin);
-    cudaFuncSetAttribute(k_eval_voxels<2>, attr, max_smem_optin);
-    cudaFuncSetAttribute(k_eval_voxels<3>, attr, max_smem_optin);
-    cudaFuncSetAttribute(k_normals, attr, max_smem_optin);
+    opt_in(k_eval_tiles<2, true>, max_smem_optin);
+    opt_in(k_eval_tiles<2, false>, max_smem_optin);
+    opt_in(k_eval_tiles<3, true>, max_smem_optin);
+    opt_in(k_eval_tiles<3, false>, max_smem_optin);
+    opt_in(k_eval_voxels<2>, max_smem_optin);
+    opt_in(k_eval_voxels<3>, max_smem_optin);
+    opt_in(k_normals, max_smem_optin);
 }
 
 template <int DIM, bool ROOT>

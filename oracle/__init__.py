@@ -5,7 +5,7 @@ ctypes loaders for
   * oracle/_ref/libmpr_ref.so      -- the unmodified reference CUDA renderer behind a C shim
                                       (ref_wrap.cu), usable only on a GPU box.
 
-Only tests/, tools/mint_golden.py, __graft_entry__.smoke() and bench.py's
+Only tests/, tools/gpu_check.py, __graft_entry__.smoke() and bench.py's
 cpu_baseline / reference legs import this package; mpr_b200/ never does.
 """
 from __future__ import annotations
@@ -204,6 +204,7 @@ def ref_lib():
         L.ref_normals.argtypes = [vp]
         L.ref_normals.restype = vp
         L.ref_num_subtapes.restype = C.c_int64
+        L.ref_download.argtypes = [vp, vp, vp]
         _ref = L
     return _ref
 
@@ -270,6 +271,15 @@ class RefGpu(_Base):
             return int((t["position"] != -1).sum())
         n_active = int(t["next"].max()) + 1 if n_prev else 0
         return n_active * 64
+
+    def download(self, image_out, normals_out=None):
+        self.L.ref_download(self.h, image_out.ctypes.data,
+                            normals_out.ctypes.data if normals_out is not None else None)
+
+    def drop_tapes(self):
+        for t in self._tapes.values():
+            self.L.ref_tape_destroy(t[0])
+        self._tapes = {}
 
     def _normals_ptr(self): return self.L.ref_normals(self.h)
     def _arena_ptr(self): return self.L.ref_tape_data(self.h)

@@ -14,7 +14,7 @@
  * PARITY STATUS: the reference ships no golden vectors or known-answer tests
  * for this path.  This restatement is pinned against
  * outputs of the unmodified reference CUDA code run on a B200
- * (tests/golden/, minted by tools/mint_golden.py through oracle/_ref).
+ * (tests/golden/, minted by tools/gpu_check.py through oracle/_ref).
  * Known, documented divergence: the float transcendentals (sinf, cosf, asinf,
  * acosf, atanf, expf, logf, powf) come from glibc here and from CUDA libdevice
  * in the reference; they may differ in the last ulp, which can flip isolated
@@ -776,4 +776,55 @@ int32_t mpro_tape_flatten(const uint64_t* arena, int32_t start, uint64_t* out, i
         if (!c_op(d)) break;
     }
     return n;
+}
+
+/* ---- unit-test hooks: single interval operators ------------------------------------------ */
+/* op codes follow the clause opcodes; unary ops ignore b; *_LI / *_IR forms take the immediate
+ * in b[0].  out = {lo, hi}; returns the min/max verdict (0 for other ops). */
+int mpro_interval_op(int op, const float* a, const float* b, float* out) {
+    const ival x = iv(a[0], a[1]);
+    const ival y = iv(b[0], b[1]);
+    const float imm = b[0];
+    ival r = x;
+    int ch = 0;
+    switch (op) {
+        case OP_SQUARE: r = iv_square(x); break;
+        case OP_SQRT: r = iv_sqrt(x); break;
+        case OP_NEG: r = iv_neg(x); break;
+        case OP_SIN: case OP_COS: r = iv(-1.0f, 1.0f); break;
+        case OP_ASIN: r = iv_asin(x); break;
+        case OP_ACOS: r = iv_acos(x); break;
+        case OP_ATAN: r = iv_atan(x); break;
+        case OP_EXP: r = iv_exp(x); break;
+        case OP_ABS: r = iv_abs(x); break;
+        case OP_LOG: r = iv_log(x); break;
+        case OP_ADD_LI: r = iv_addf(x, imm); break;
+        case OP_ADD_LR: r = iv_add(x, y); break;
+        case OP_MUL_LI: r = iv_mulf(x, imm); break;
+        case OP_MUL_LR: r = iv_mul(x, y); break;
+        case OP_MIN_LI: r = iv_min(x, iv(imm, imm), &ch); break;
+        case OP_MIN_LR: r = iv_min(x, y, &ch); break;
+        case OP_MAX_LI: r = iv_max(x, iv(imm, imm), &ch); break;
+        case OP_MAX_LR: r = iv_max(x, y, &ch); break;
+        case OP_SUB_LI: r = iv_subf(x, imm); break;
+        case OP_SUB_IR: r = iv_fsub(imm, x); break;
+        case OP_SUB_LR: r = iv_sub(x, y); break;
+        case OP_DIV_LI: r = iv_divf(x, imm); break;
+        case OP_DIV_IR: r = iv_div(iv(imm, imm), x); break;
+        case OP_DIV_LR: r = iv_div(x, y); break;
+        default: break;
+    }
+    fesetround(FE_TONEAREST);
+    out[0] = r.lo; out[1] = r.hi;
+    return ch;
+}
+
+/* Evaluates a whole tape at n points in float (the float-stage clause semantics). */
+void mpro_eval_points(const uint64_t* tape, const float* xyz, int64_t n, float* out) {
+    fesetround(FE_TONEAREST);
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        unsigned work = 0;
+        out[i] = eval_tape_float(tape, 0, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &work);
+    }
 }

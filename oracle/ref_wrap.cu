@@ -75,4 +75,13 @@ int32_t ref_num_active(void* c) { return *static_cast<mpr::Context*>(c)->num_act
 uint32_t* ref_normals(void* c) { return static_cast<mpr::Context*>(c)->normals.get(); }
 int64_t ref_num_subtapes(void) { return NUM_SUBTAPES; }
 
+// Bench helper: copies the final image (and normals) to host buffers with cudaMemcpy, the
+// cheapest way to read the reference's managed result buffers from the host.
+void ref_download(void* c, int32_t* image_out, uint32_t* normals_out) {
+    mpr::Context* ctx = static_cast<mpr::Context*>(c);
+    const size_t n = size_t(ctx->image_size_px) * ctx->image_size_px;
+    if (image_out) cudaMemcpy(image_out, ctx->stages[3].filled.get(), n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (normals_out) cudaMemcpy(normals_out, ctx->normals.get(), n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+}
+
 }  // extern "C"

@@ -1,0 +1,174 @@
+"""GPU parity tests (B200 box): libmprb through its C ABI against
+  (1) fixtures minted from the unmodified reference build (tests/golden/ref),
+  (2) the reference build itself when oracle/_ref/libmpr_ref.so travelled with the snapshot,
+  (3) the CPU restatement,
+and size-independent properties at the BASELINE sizes.  Integer / byte results: bit exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+import parity
+from conftest import golden_cases, load_tape
+from mpr_b200 import capi, sharding
+
+pytestmark = pytest.mark.gpu
+SUBTAPES = 6400000
+CASES = golden_cases()
+SMALL = [c for c in CASES if c[5] is not None]
+
+
+def render(model, dim, size, **kw):
+    ctx = capi.Context(size, num_subtapes=kw.pop("num_subtapes", SUBTAPES), **kw)
+    tape = capi.Tape(load_tape(model))
+    (ctx.render2D if dim == 2 else ctx.render3D)(tape)
+    return ctx, tape
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_matches_reference_fixture(case):
+    name, model, dim, size, summary, npz = case
+    ctx, tape = render(model, dim, size)
+    fp = parity.fingerprint(ctx, dim)
+    got = parity.summarize(fp)
+    bad = parity.compare_summary(summary, got)
+    assert not bad, bad
+    if npz is not None:
+        ref = dict(np.load(npz))
+        ref["dim"], ref["size"] = dim, size
+        assert not parity.compare(ref, fp)
+    st = ctx.stats()
+    assert st.overflow == 0 and st.n_launches > 0
+    ctx.close()
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("model,dim,size", [("prospero", 2, 512), ("involute_gear_2d", 2, 1024),
+                                            ("architecture", 3, 512), ("bear", 3, 512),
+                                            ("involute_gear_3d", 3, 512)])
+def test_matches_live_reference_build(model, dim, size):
+    cells = load_tape(model)
+    ref = oracle.RefGpu(size)
+    (ref.render2D if dim == 2 else ref.render3D)(cells)
+    ref_fp = parity.fingerprint(ref, dim)
+    ref.close()
+    ctx, tape = render(model, dim, size)
+    assert not parity.compare(ref_fp, parity.fingerprint(ctx, dim))
+    ctx.close()
+
+
+@pytest.mark.parametrize("model,dim,size", [("hello_world", 2, 128), ("prospero", 2, 256), ("hello_world", 3, 128),
+                                            ("architecture", 3, 128)])
+def test_matches_cpu_restatement(model, dim, size):
+    o = oracle.CpuOracle(size, SUBTAPES)
+    (o.render2D if dim == 2 else o.render3D)(load_tape(model))
+    ctx, tape = render(model, dim, size)
+    assert not parity.compare(parity.fingerprint(o, dim), parity.fingerprint(ctx, dim))
+    o.close()
+    ctx.close()
+
+
+def test_view_matrix_and_z_plane_are_honoured():
+    # a rotated / translated / perspective view must go through the same interval transform
+    m3 = np.array([[0.8, -0.3, 0.1], [0.3, 0.8, -0.2], [0.05, 0.02, 1.0]], dtype=np.float32)
+    cells = load_tape("hello_world")
+    o = oracle.CpuOracle(256)
+    o.render2D(cells, mat=m3, z=0.25)
+    ctx = capi.Context(256)
+    tape = capi.Tape(cells)
+    ctx.render2D(tape, mat=m3, z=0.25)
+    assert not parity.compare(parity.fingerprint(o, 2), parity.fingerprint(ctx, 2))
+    m4 = np.eye(4, dtype=np.float32)
+    m4[0, 1], m4[1, 0], m4[3, 2], m4[2, 3] = 0.2, -0.2, 0.4, 0.1
+    o3 = oracle.CpuOracle(128)
+    o3.render3D(cells, mat=m4)
+    ctx3 = capi.Context(128)
+    ctx3.render3D(tape, mat=m4)
+    assert not parity.compare(parity.fingerprint(o3, 3), parity.fingerprint(ctx3, 3))
+
+
+def test_frames_are_idempotent_and_contexts_reusable():
+    ctx, tape = render("architecture", 3, 256)
+    a = parity.fingerprint(ctx, 3)
+    ctx.render3D(tape)
+    assert not parity.compare(a, parity.fingerprint(ctx, 3))
+    # a different model, then back again, in the same context
+    other = capi.Tape(load_tape("bear"))
+    ctx.render3D(other)
+    ctx.render3D(tape)
+    assert not parity.compare(a, parity.fingerprint(ctx, 3))
+    # 2D after 3D in the same context
+    ctx.render2D(capi.Tape(load_tape("prospero")))
+    ref2, _ = render("prospero", 2, 256)
+    assert np.array_equal(ctx.image(), ref2.image())
+
+
+def test_host_buffer_entry_points_equal_device_ones():
+    cells = load_tape("bear")
+    ctx, tape = render("bear", 3, 256)
+    depth = np.zeros((256, 256), dtype=np.int32)
+    norm = np.zeros((256, 256), dtype=np.uint32)
+    ctx2 = capi.Context(256, num_subtapes=SUBTAPES)
+    ctx2.render3D_host(cells, depth, norm)
+    assert np.array_equal(depth, ctx.image()) and np.array_equal(norm, ctx.normals())
+    img = np.zeros((512, 512), dtype=np.int32)
+    c2 = capi.Context(512)
+    c2.render2D_host(load_tape("prospero"), img)
+    ref, _ = render("prospero", 2, 512)
+    assert np.array_equal(img, ref.image())
+    assert set(np.unique(img)) <= {0, 1}
+
+
+@pytest.mark.parametrize("model,dim,size,world", [("prospero", 2, 1024, 4), ("bear", 3, 256, 2), ("architecture", 3, 512, 8)])
+def test_row_bands_tile_the_full_frame(model, dim, size, world):
+    """Sharding property: rendering tile-row bands separately and stacking them equals one full frame."""
+    full, tape = render(model, dim, size)
+    img = np.zeros((size, size), dtype=np.int32)
+    nrm = np.zeros((size, size), dtype=np.uint32)
+    for r in range(world):
+        b, e = sharding.band_rows(size, world, r)
+        part = capi.Context(size, num_subtapes=SUBTAPES, row_begin=b, row_end=e)
+        (part.render2D if dim == 2 else part.render3D)(tape)
+        sl = sharding.band_slice(size, world, r)
+        img[sl] = part.image()[sl]
+        if dim == 3:
+            nrm[sl] = part.normals()[sl]
+        outside = np.ones(size, dtype=bool)
+        outside[sl] = False
+        assert not part.image()[outside].any()          # a band context never writes other bands
+        part.close()
+    assert np.array_equal(img, full.image())
+    if dim == 3:
+        assert np.array_equal(nrm, full.normals())
+
+
+def test_arena_exhaustion_degrades_like_the_reference():
+    """With a tiny arena, tiles keep their parent tape (reference context.cu:336-347); the image
+    is still correct because every tape that was kept is valid for its tile."""
+    full, tape = render("prospero", 2, 512)
+    small = capi.Context(512, num_subtapes=200)
+    small.render2D(tape)
+    assert np.array_equal(small.image(), full.image())
+    assert small.stats().tape_index >= 200 * 64 - 64 * 64
+
+
+def test_full_size_headline_configs():
+    """BASELINE configs at full size: golden hash + structural properties."""
+    ctx, tape = render("prospero", 2, 4096)
+    img = ctx.image()
+    assert set(np.unique(img)) <= {0, 1}
+    st = ctx.stats()
+    assert st.n_active[0] > 0 and st.n_active[1] > 0
+    # every filled level-0 tile shows up as a fully set 64x64 block of the final image
+    f0 = ctx.filled(0)
+    ys, xs = np.nonzero(f0)
+    for y, x in list(zip(ys, xs))[:50]:
+        assert img[y * 64:(y + 1) * 64, x * 64:(x + 1) * 64].all()
+    ctx.close()
+    ctx, tape = render("bear", 3, 1024)
+    h = ctx.image()
+    n = ctx.normals()
+    assert h.max() < 1024 and ((h != 0) == (n != 0)).all()     # a normal exactly where there is depth
+    assert ((n >> 24) == 0xFF)[n != 0].all()
+    ctx.close()

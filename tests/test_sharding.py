@@ -1,0 +1,54 @@
+"""N>1 host path on CPU: band partition + single all-gather over gloo, world_size 2."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_tape
+from mpr_b200 import sharding
+
+
+def test_band_rows_partition_the_image():
+    for size, world in [(1024, 2), (1024, 8), (4096, 8), (2048, 4)]:
+        rows = [sharding.band_rows(size, world, r) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == size // 64
+        assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
+    with pytest.raises(ValueError):
+        sharding.band_rows(1024 + 64, 2, 0)    # 17 rows do not split in two
+
+
+def _worker(rank, world, port, size, full_path, out_path):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.from_numpy(np.load(full_path))
+    local = torch.zeros_like(full)
+    sl = sharding.band_slice(size, world, rank)
+    local[sl] = full[sl]                        # this rank only "rendered" its band
+    got = sharding.all_gather_bands(local, size)
+    ok = bool(torch.equal(got, full))
+    np.save(out_path.format(rank), np.array([ok]))
+    dist.destroy_process_group()
+
+
+def test_all_gather_reassembles_the_frame_gloo(tmp_path):
+    import oracle
+    import torch.multiprocessing as mp
+    size = 256
+    o = oracle.CpuOracle(size)
+    o.render2D(load_tape("hello_world"))
+    full = np.array(o.image(), dtype=np.int32)
+    o.close()
+    fp = tmp_path / "full.npy"
+    np.save(fp, full)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "ok{}.npy")
+    mp.spawn(_worker, args=(2, port, size, str(fp), out), nprocs=2, join=True)
+    assert all(bool(np.load(out.format(r))[0]) for r in range(2))
