@@ -74,6 +74,13 @@ struct mprb_tape {
     uint64_t* cells = nullptr;   // managed
     int32_t length = 0;
     int32_t n_slots = 0;
+    // Clause-parallel plan for the root level (see k_eval_root)
+    RootClause* sched = nullptr;        // device
+    int32_t* level_start = nullptr;     // device
+    int32_t n_levels = 0;
+    int32_t result_v = 0;
+    int32_t group = 0;                  // threads per tile; 0 = no plan (serial root walk)
+    int32_t smem_per_tile = 0;
 };
 
 struct mprb_ctx {
@@ -103,7 +110,11 @@ struct mprb_ctx {
     FrameCtl* ctl_host = nullptr;    // pinned
     uint64_t* stage_cells = nullptr; // pinned staging for host tapes
     int32_t stage_cells_cap = 0;
-    bool have_3d = false;
+    bool serial_root = false;        // debugging / A-B switch: MPRB_SERIAL_ROOT=1
+    // Host-buffer entry points: the per-tape root plan is cached across frames as long as
+    // the caller keeps passing the same cells (the cells themselves are re-uploaded every frame).
+    mprb_tape* host_plan = nullptr;
+    std::vector<uint64_t> host_plan_cells;
 
     mprb_frame_stats stats = {};
     std::map<long long, int> occ_cache;
@@ -136,6 +147,60 @@ int validate_tape(const uint64_t* cells, int32_t n) {
     if (tape_num_slots(cells, n) > 128)
         return fail(MPRB_E_ARG, "tape uses more than 128 slots (the reference kernels hold 128)");
     return MPRB_OK;
+}
+
+// Root tape -> SSA + dependency levels.  Value ids: 0 = none, 1..3 = x, y, z, 3+i = clause i.
+// Within a level clauses are ordered by opcode so that neighbouring lanes mostly run the
+// same interval operator.
+struct RootPlan {
+    std::vector<RootClause> sched;
+    std::vector<int32_t> level_start;
+    int result_v = 0;
+};
+
+RootPlan build_root_plan(const uint64_t* cells, int32_t n_cells) {
+    const int n = n_cells - 2;
+    RootPlan p;
+    std::vector<int> writer(256, 0);          // slot -> value id that currently lives there
+    const uint32_t hdr = uint32_t(cells[0]);
+    // same binding order as the kernels: x, then y, then z (a later axis wins a shared slot)
+    const int ax[3] = {int((hdr >> 8) & 0xff), int((hdr >> 16) & 0xff), int(hdr >> 24)};
+    for (int k = 0; k < 3; ++k) if (ax[k]) writer[ax[k]] = 1 + k;
+    std::vector<int> depth(n + 4, 0);
+    std::vector<RootClause> byidx(n + 1);
+    int n_choice = 0, max_depth = 0;
+    for (int i = 1; i <= n; ++i) {
+        const uint64_t d = cells[i];
+        const uint32_t w = uint32_t(d);
+        const uint32_t op = w & 0xff, out = (w >> 8) & 0xff, lhs = (w >> 16) & 0xff, rhs = w >> 24;
+        RootClause rc;
+        rc.lsrc = lhs ? uint32_t(writer[lhs]) : 0u;
+        rc.rsrc = rhs ? uint32_t(writer[rhs]) : 0u;
+        uint32_t hi = uint32_t(d >> 32);
+        memcpy(&rc.imm, &hi, 4);
+        const bool is_choice = op >= OP_MIN_LI && op <= OP_MAX_LR;
+        const bool past_cap = is_choice && n_choice >= kMaxChoices;
+        n_choice += is_choice;
+        rc.op_idx = op | (past_cap ? 0x100u : 0u) | (uint32_t(i) << 12);
+        byidx[i] = rc;
+        const int dep = 1 + std::max(depth[rc.lsrc], depth[rc.rsrc]);
+        depth[3 + i] = dep;
+        max_depth = std::max(max_depth, dep);
+        writer[out] = 3 + i;
+    }
+    p.result_v = writer[(uint32_t(cells[n + 1]) >> 8) & 0xff];
+    std::vector<std::vector<int>> levels(max_depth + 1);
+    for (int i = 1; i <= n; ++i) levels[depth[3 + i]].push_back(i);
+    p.level_start.push_back(0);
+    for (int L = 1; L <= max_depth; ++L) {
+        auto& v = levels[L];
+        std::stable_sort(v.begin(), v.end(), [&](int x, int y) {
+            return (byidx[x].op_idx & 0xff) < (byidx[y].op_idx & 0xff);
+        });
+        for (int i : v) p.sched.push_back(byidx[i]);
+        p.level_start.push_back(int32_t(p.sched.size()));
+    }
+    return p;
 }
 
 int ensure_stage(mprb_ctx* c, int stage, long long cap) {
@@ -177,7 +242,7 @@ struct Timer {
 // The frame proper.  `cells` may be a device/managed pointer (async D2D copy)
 // or a host pointer (async H2D copy through pinned staging).
 int render(mprb_ctx* c, int dim, const uint64_t* cells, int32_t n_cells, bool cells_on_host,
-           int n_slots, const float* matrix, float z)
+           int n_slots, const float* matrix, float z, const mprb_tape* plan = nullptr)
 {
     if (!c) return fail(MPRB_E_ARG, "null context");
     const int S = c->size;
@@ -262,12 +327,35 @@ int render(mprb_ctx* c, int dim, const uint64_t* cells, int32_t n_cells, bool ce
         ea.level = l;
         ea.n_slots = n_slots;
         ea.z = z;
-        int grid = c->sm_count * cached_occupancy(c, 0, dim, root, n_slots);
-        if (root) {
-            const long long items = (count0 + 31) / 32;
-            grid = int(std::min<long long>(grid, (items + kEvalWarps - 1) / kEvalWarps));
+        if (root && plan && plan->group > 0 && !c->serial_root) {
+            EvalRootArgs ra = {};
+            ra.arena = c->arena;
+            ra.tape_index = &c->ctl->tape_cursor;
+            ra.arena_cap = int32_t(c->arena_cells);
+            ra.image = c->filled[st];
+            ra.tiles = c->tiles[st];
+            ra.tps = uint32_t(tps);
+            ra.count0 = int32_t(count0);
+            ra.row_begin = c->row_begin;
+            ra.row_end = c->row_end;
+            ra.ctl = c->ctl;
+            ra.sched = plan->sched;
+            ra.level_start = plan->level_start;
+            ra.n_levels = plan->n_levels;
+            ra.n_clauses = n_cells - 2;
+            ra.result_v = plan->result_v;
+            ra.group = plan->group;
+            ra.smem_per_tile = plan->smem_per_tile;
+            ra.z = z;
+            launch_eval_root(dim, ra, mat, s);
+        } else {
+            int grid = c->sm_count * cached_occupancy(c, 0, dim, root, n_slots);
+            if (root) {
+                const long long items = (count0 + 31) / 32;
+                grid = int(std::min<long long>(grid, (items + kEvalWarps - 1) / kEvalWarps));
+            }
+            launch_eval_tiles(dim, root, ea, mat, std::max(grid, 1), s);
         }
-        launch_eval_tiles(dim, root, ea, mat, std::max(grid, 1), s);
         tm.mark();
 
         RankArgs ra = {};
@@ -309,7 +397,9 @@ int render(mprb_ctx* c, int dim, const uint64_t* cells, int32_t n_cells, bool ce
         va.queue = &c->ctl->queue[q++];
         va.n_slots = n_slots;
         va.z = z;
-        launch_eval_voxels(dim, va, mat, c->sm_count * cached_occupancy(c, 1, dim, false, n_slots), s);
+        const int grid = c->sm_count * cached_occupancy(c, 1, dim, false, n_slots);
+        if (dim == 2) launch_eval_pixels(va, m3, grid, s);
+        else launch_eval_voxels(va, m4, grid, s);
         tm.mark();
     }
     if (dim == 3) {
@@ -334,6 +424,17 @@ int render(mprb_ctx* c, int dim, const uint64_t* cells, int32_t n_cells, bool ce
     c->stats.n_launches = tm.n - 1;
     MPRB_CUDA(cudaGetLastError());
     return MPRB_OK;
+}
+
+const mprb_tape* host_plan_for(mprb_ctx* c, const uint64_t* cells, int32_t n) {
+    if (c->host_plan && int32_t(c->host_plan_cells.size()) == n &&
+        memcmp(c->host_plan_cells.data(), cells, sizeof(uint64_t) * size_t(n)) == 0)
+        return c->host_plan;
+    if (c->host_plan) mprb_tape_destroy(c->host_plan);
+    c->host_plan = nullptr;
+    if (mprb_tape_create(cells, n, &c->host_plan) != MPRB_OK) return nullptr;
+    c->host_plan_cells.assign(cells, cells + n);
+    return c->host_plan;
 }
 
 // Waits for the frame and publishes the counters.
@@ -405,6 +506,7 @@ int mprb_ctx_create(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx**
     c->device = device;
     c->size = image_size_px;
     const int tps0 = image_size_px / 64;
+    c->serial_root = getenv("MPRB_SERIAL_ROOT") != nullptr;
     c->row_begin = opts ? opts->row_begin : 0;
     c->row_end = (opts && opts->row_end > 0) ? opts->row_end : tps0;
     if (c->row_begin < 0 || c->row_end > tps0 || c->row_begin >= c->row_end) {
@@ -486,6 +588,7 @@ void mprb_ctx_destroy(mprb_ctx* c) {
     if (c->ctl) cudaFree(c->ctl);
     if (c->ctl_host) cudaFreeHost(c->ctl_host);
     if (c->stage_cells) cudaFreeHost(c->stage_cells);
+    if (c->host_plan) mprb_tape_destroy(c->host_plan);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     for (auto& ev : c->ev_k) if (ev) cudaEventDestroy(ev);
@@ -529,6 +632,32 @@ int mprb_tape_create(const uint64_t* host_cells, int32_t n_cells, mprb_tape** ou
     }
     t->length = n_cells;
     t->n_slots = tape_num_slots(host_cells, n_cells);
+    if (n_cells > 2 && n_cells - 2 < (1 << 20)) {
+        const RootPlan plan = build_root_plan(host_cells, n_cells);
+        const int n = n_cells - 2;
+        const int levels = int(plan.level_start.size()) - 1;
+        // Threads per tile ~ clauses per level, so that a level is one pass
+        int group = 32;
+        while (group < kRootThreads && group < n / std::max(levels, 1)) group *= 2;
+        const int per_tile = ((n + 4) * 10 + 64 + 15) / 16 * 16;
+        int max_smem = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        while (group < kRootThreads && (kRootThreads / group) * per_tile > max_smem) group *= 2;
+        if (per_tile <= max_smem && plan.result_v != 0) {
+            cudaError_t e1 = cudaMalloc(&t->sched, sizeof(RootClause) * plan.sched.size());
+            cudaError_t e2 = cudaMalloc(&t->level_start, sizeof(int32_t) * plan.level_start.size());
+            if (e1 == cudaSuccess && e2 == cudaSuccess) {
+                cudaMemcpy(t->sched, plan.sched.data(), sizeof(RootClause) * plan.sched.size(), cudaMemcpyHostToDevice);
+                cudaMemcpy(t->level_start, plan.level_start.data(), sizeof(int32_t) * plan.level_start.size(),
+                           cudaMemcpyHostToDevice);
+                t->n_levels = levels;
+                t->result_v = plan.result_v;
+                t->group = group;
+                t->smem_per_tile = per_tile;
+            }
+        }
+    }
     *out = t;
     return MPRB_OK;
 }
@@ -536,6 +665,8 @@ int mprb_tape_create(const uint64_t* host_cells, int32_t n_cells, mprb_tape** ou
 void mprb_tape_destroy(mprb_tape* t) {
     if (!t) return;
     if (t->cells) cudaFree(t->cells);
+    if (t->sched) cudaFree(t->sched);
+    if (t->level_start) cudaFree(t->level_start);
     delete t;
 }
 
@@ -545,13 +676,13 @@ int32_t mprb_tape_num_slots(const mprb_tape* t) { return t ? t->n_slots : 0; }
 
 int mprb_render2d(mprb_ctx* c, const mprb_tape* t, const float mat3[9], float z) {
     if (!c || !t || !mat3) return fail(MPRB_E_ARG, "null argument");
-    if (int e = render(c, 2, t->cells, t->length, false, t->n_slots, mat3, z)) return e;
+    if (int e = render(c, 2, t->cells, t->length, false, t->n_slots, mat3, z, t)) return e;
     return finish(c, 2);
 }
 
 int mprb_render3d(mprb_ctx* c, const mprb_tape* t, const float mat4[16]) {
     if (!c || !t || !mat4) return fail(MPRB_E_ARG, "null argument");
-    if (int e = render(c, 3, t->cells, t->length, false, t->n_slots, mat4, 0.0f)) return e;
+    if (int e = render(c, 3, t->cells, t->length, false, t->n_slots, mat4, 0.0f, t)) return e;
     return finish(c, 3);
 }
 
@@ -559,7 +690,8 @@ int mprb_render2d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
                        const float mat3[9], float z, int32_t* image_out) {
     if (!c || !mat3) return fail(MPRB_E_ARG, "null argument");
     if (int e = validate_tape(host_cells, n_cells)) return e;
-    if (int e = render(c, 2, host_cells, n_cells, true, tape_num_slots(host_cells, n_cells), mat3, z)) return e;
+    if (int e = render(c, 2, host_cells, n_cells, true, tape_num_slots(host_cells, n_cells), mat3, z,
+                       host_plan_for(c, host_cells, n_cells))) return e;
     const size_t n = size_t(c->size) * c->size;
     if (image_out)
         MPRB_CUDA(cudaMemcpyAsync(image_out, c->filled[3], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -570,7 +702,8 @@ int mprb_render3d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
                        const float mat4[16], int32_t* depth_out, uint32_t* normals_out) {
     if (!c || !mat4) return fail(MPRB_E_ARG, "null argument");
     if (int e = validate_tape(host_cells, n_cells)) return e;
-    if (int e = render(c, 3, host_cells, n_cells, true, tape_num_slots(host_cells, n_cells), mat4, 0.0f)) return e;
+    if (int e = render(c, 3, host_cells, n_cells, true, tape_num_slots(host_cells, n_cells), mat4, 0.0f,
+                       host_plan_for(c, host_cells, n_cells))) return e;
     const size_t n = size_t(c->size) * c->size;
     if (depth_out)
         MPRB_CUDA(cudaMemcpyAsync(depth_out, c->filled[3], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));

@@ -14,8 +14,9 @@
 //       and the TileNode write-back are fused in.
 //   k_rank_tiles              occlusion post-mask + compaction of survivors
 //   k_upsample_filled         filled image -> next level's image
-//   k_eval_voxels<DIM>        float pass: a warp owns one 64-sample tile,
-//                             two samples per lane
+//   k_eval_pixels             2D float pass: a warp owns one 8x8 tile, two pixels per lane
+//   k_eval_voxels             3D float pass: a warp owns one 4x4x4 tile, two voxels per lane
+//   k_eval_root<DIM>          root level, clause-parallel over an SSA / levelised root tape
 //   k_normals                 per-pixel gradient pass, lanes grouped by tape
 //
 // Behaviour (what is computed, bit for bit) follows the reference kernels in
@@ -445,6 +446,273 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
 }
 
 ////////////////////////////////////////////////////////////////////////////////
+// Root level, evaluated clause-parallel.
+//
+// All top-level tiles run the SAME tape, and there are few of them, so walking
+// it one clause at a time (k_eval_tiles<DIM, true>) leaves the machine idle
+// behind a dependent chain of thousands of clauses.  Here a group of G threads
+// owns ONE tile and evaluates the tape in dependency-level order instead: the
+// host turns the root tape into SSA form once per Tape (every operand names the
+// clause that produced it, not a reused slot) and buckets clauses by depth, so
+// a level is |level| independent interval operations.  Interval results do not
+// depend on evaluation order, so every value, verdict and classification is the
+// one the serial walk produces.
+//
+// The shortened tape is produced by the same mark-and-sweep as the serial push
+// (context.cu:323-458), expressed on SSA ids: marks propagate from the result
+// back through the levels, then kept clauses are compacted IN TAPE ORDER with a
+// group-wide prefix sum and written as one contiguous run (header, clauses, end
+// cell) - a valid tape in the reference's format that simply needs no JUMP.
+
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(kRootThreads)
+k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
+{
+    extern __shared__ __align__(16) unsigned char s_root[];
+    const int G = a.group;
+    const int gid = threadIdx.x / G;
+    const int t = threadIdx.x % G;
+    const int bar = gid + 1;
+    const int n = a.n_clauses;
+    const int nv = n + 4;                                   // value ids: 0 none, 1..3 axes, 3+i clause i
+    unsigned char* const mine = s_root + size_t(gid) * a.smem_per_tile;
+    float2* const V = reinterpret_cast<float2*>(mine);
+    uint8_t* const C = mine + size_t(nv) * 8;               // min/max verdict per clause
+    uint8_t* const A = C + nv;                              // liveness per value id
+    int* const scratch = reinterpret_cast<int*>(mine + a.smem_per_tile - 64);
+    uint64_t* const arena = a.arena;
+    const uint32_t tps = a.tps;
+
+    int tile = blockIdx.x * (kRootThreads / G) + gid;
+    if (tile >= a.count0) return;
+    if (DIM == 3) tile = a.count0 - 1 - tile;               // highest z first
+    const int sx = tile % tps, sy = (tile / tps) % tps, sz = DIM == 3 ? (tile / tps) / tps : 0;
+    const int img_index = sx + sy * tps;
+
+    // Occlusion pre-mask.  The image changes under us (other tiles' atomicMax), so one
+    // thread looks and the whole group follows its answer.
+    if (t == 0) {
+        bool al = (sy >= a.row_begin) && (sy < a.row_end);
+        if (DIM == 3 && al && __ldcg(&a.image[img_index]) > sz) al = false;
+        scratch[12] = al;
+        if (!al) {
+            a.tiles[tile].position = -1;
+            a.tiles[tile].tape = 0;
+            a.tiles[tile].next = -1;
+        }
+    }
+    group_sync(bar, G);
+    if (!scratch[12]) return;
+
+    if (t == 0) {                                            // tile box -> axis intervals
+        const float ftps = float(tps);
+        const ival ix = iv(tile_edge(sx, ftps), tile_edge(sx + 1, ftps));
+        const ival iy = iv(tile_edge(sy, ftps), tile_edge(sy + 1, ftps));
+        const float* m = mat.d;
+        if (DIM == 3) {
+            const ival iz = iv(tile_edge(sz, ftps), tile_edge(sz + 1, ftps));
+            ival r[4];
+            #pragma unroll
+            for (int i = 0; i < 4; ++i)
+                r[i] = iv_add(iv_add(iv_add(iv_mul(ix, m[i]), iv_mul(iy, m[4 + i])), iv_mul(iz, m[8 + i])), m[12 + i]);
+            V[1] = iv_div(r[0], r[3]);
+            V[2] = iv_div(r[1], r[3]);
+            V[3] = iv_div(r[2], r[3]);
+        } else {
+            ival r[3];
+            #pragma unroll
+            for (int i = 0; i < 3; ++i)
+                r[i] = iv_add(iv_add(iv_mul(ix, m[i]), iv_mul(iy, m[3 + i])), m[6 + i]);
+            V[1] = iv_div(r[0], r[2]);
+            V[2] = iv_div(r[1], r[2]);
+            V[3] = iv(a.z, a.z);
+        }
+        V[0] = iv(0.0f, 0.0f);
+        scratch[0] = 0;                                      // any verdict decided?
+    }
+    for (int i = t; i < nv; i += G) A[i] = 0;
+    group_sync(bar, G);
+
+    // ---- forward: one dependency level at a time ---------------------------------------
+    bool any_choice = false;
+    for (int L = 0; L < a.n_levels; ++L) {
+        const int k_end = a.level_start[L + 1];
+        for (int k = a.level_start[L] + t; k < k_end; k += G) {
+            const RootClause rc = a.sched[k];
+            const uint32_t op = rc.op_idx & 0xff;
+            const uint32_t idx = rc.op_idx >> 12;
+            const float imm = rc.imm;
+            const ival Lv = V[rc.lsrc];
+            const ival Rv = V[rc.rsrc];
+            ival o;
+            int c = 0;
+            switch (op) {
+                case OP_SQUARE: o = iv_square(Lv); break;
+                case OP_SQRT:   o = iv_sqrt(Lv); break;
+                case OP_NEG:    o = iv_neg(Lv); break;
+                case OP_SIN:    o = iv_sin(Lv); break;
+                case OP_COS:    o = iv_cos(Lv); break;
+                case OP_ASIN:   o = iv_asin(Lv); break;
+                case OP_ACOS:   o = iv_acos(Lv); break;
+                case OP_ATAN:   o = iv_atan(Lv); break;
+                case OP_EXP:    o = iv_exp(Lv); break;
+                case OP_ABS:    o = iv_abs(Lv); break;
+                case OP_LOG:    o = iv_log(Lv); break;
+                case OP_ADD_LI: o = iv_add(Lv, imm); break;
+                case OP_ADD_LR: o = iv_add(Lv, Rv); break;
+                case OP_MUL_LI: o = iv_mul(Lv, imm); break;
+                case OP_MUL_LR: o = iv_mul(Lv, Rv); break;
+                case OP_MIN_LI: o = iv_min(Lv, iv(imm, imm), c); break;
+                case OP_MIN_LR: o = iv_min(Lv, Rv, c); break;
+                case OP_MAX_LI: o = iv_max(Lv, iv(imm, imm), c); break;
+                case OP_MAX_LR: o = iv_max(Lv, Rv, c); break;
+                case OP_SUB_LI: o = iv_sub(Lv, imm); break;
+                case OP_SUB_IR: o = iv_sub(imm, Rv); break;
+                case OP_SUB_LR: o = iv_sub(Lv, Rv); break;
+                case OP_DIV_LI: o = iv_div(Lv, imm); break;
+                case OP_DIV_IR: o = iv_div(imm, Rv); break;
+                case OP_DIV_LR: o = iv_div(Lv, Rv); break;
+                default: o = Lv; break;
+            }
+            V[3 + idx] = o;
+            if (op >= OP_MIN_LI && op <= OP_MAX_LR) {
+                any_choice |= (c != 0);
+                // verdicts past the reference's 4096-entry record count as "undecided" when
+                // the tape is shortened, but still make the tile eligible (context.cu:254-263)
+                C[idx] = (rc.op_idx & 0x100u) ? 0 : uint8_t(c);
+            }
+        }
+        group_sync(bar, G);
+    }
+    if (any_choice) scratch[0] = 1;                          // benign same-value race
+    const ival result = V[a.result_v];
+    group_sync(bar, G);
+    any_choice = scratch[0] != 0;
+
+    // ---- classify (context.cu:289-321) ---------------------------------------------------
+    int out_position = -1;
+    bool pushing = false;
+    if (result.x > 0.0f) {
+        // empty
+    } else if (DIM == 3 && __ldcg(&a.image[img_index]) > sz) {
+        // hidden (the value may change concurrently, so let one thread decide for the group)
+    } else if (result.y < 0.0f) {
+        if (t == 0) {
+            if (DIM == 3) atomicMax(&a.image[img_index], sz);
+            else a.image[img_index] = 1;
+        }
+    } else {
+        out_position = tile;
+        pushing = any_choice;
+    }
+    if (DIM == 3) {   // make the racy "hidden" test group-uniform: thread 0's view wins
+        if (t == 0) { scratch[1] = out_position; scratch[2] = pushing; }
+        group_sync(bar, G);
+        out_position = scratch[1];
+        pushing = scratch[2] != 0;
+    }
+    int out_tape = 0;
+
+    if (pushing) {
+        // ---- mark: result -> operands, top level first ------------------------------------
+        if (t == 0) A[a.result_v] = 1;
+        group_sync(bar, G);
+        for (int L = a.n_levels - 1; L >= 0; --L) {
+            const int k_end = a.level_start[L + 1];
+            for (int k = a.level_start[L] + t; k < k_end; k += G) {
+                const RootClause rc = a.sched[k];
+                const uint32_t op = rc.op_idx & 0xff;
+                const uint32_t idx = rc.op_idx >> 12;
+                if (!A[3 + idx]) continue;
+                const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[idx] : 0;
+                if (c == 0) { A[rc.lsrc] = 1; A[rc.rsrc] = 1; }
+                else if (c == 1) { A[rc.lsrc] = 1; }
+                else { A[rc.rsrc] = 1; }                     // rsrc == 0 for immediate forms
+            }
+            group_sync(bar, G);
+        }
+        // ---- sweep: compact kept clauses in tape order ---------------------------------------
+        const int per = (n + G - 1) / G;
+        const int i_begin = 1 + t * per, i_end = min(n + 1, i_begin + per);
+        int kept = 0;
+        for (int i = i_begin; i < i_end; ++i) {
+            if (!A[3 + i]) continue;
+            const uint32_t w = uint32_t(arena[i]);
+            const uint32_t op = w & 0xff, i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
+            const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[i] : 0;
+            const bool dropped = (c == 1 && i_lhs == i_out) || (c == 2 && i_rhs != 0 && i_rhs == i_out);
+            kept += dropped ? 0 : 1;
+        }
+        // group-wide exclusive scan of `kept`
+        int incl = kept;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, o);
+            if ((t & 31) >= o) incl += v;
+        }
+        int* const wsum = scratch + 4;                        // up to 8 warps per group
+        if ((t & 31) == 31) wsum[t >> 5] = incl;
+        group_sync(bar, G);
+        int offset = incl - kept, total = 0;
+        for (int wv = 0; wv < G / 32; ++wv) {
+            const int s = wsum[wv];
+            if (wv < (t >> 5)) offset += s;
+            total += s;
+        }
+        if (t == 0) {
+            const int need = (total + 2 + kChunk - 1) / kChunk * kChunk;
+            int base = -1;
+            if (*(volatile int32_t*)a.tape_index < a.arena_cap) {
+                base = atomicAdd(a.tape_index, need);
+                if (base + need >= a.arena_cap) base = -1;     // arena exhausted: keep the root tape
+            }
+            scratch[3] = base;
+        }
+        group_sync(bar, G);
+        const int base = scratch[3];
+        if (base >= 0) {
+            int o = base + 1 + offset;
+            for (int i = i_begin; i < i_end; ++i) {
+                if (!A[3 + i]) continue;
+                uint64_t d = arena[i];
+                const uint32_t w = uint32_t(d);
+                const uint32_t op = w & 0xff, i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
+                const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[i] : 0;
+                if (c == 1) {
+                    if (i_lhs == i_out) continue;
+                    d = (d & ~0xffull) | OP_COPY_LHS;
+                } else if (c == 2) {
+                    if (i_rhs != 0 && i_rhs == i_out) continue;
+                    d = (d & ~0xffull) | (i_rhs ? OP_COPY_RHS : OP_COPY_IMM);
+                }
+                arena[o++] = d;
+            }
+            if (t == 0) {
+                arena[base] = arena[0];                       // header
+                arena[base + total + 1] = arena[n + 1];       // end cell
+            }
+            out_tape = base;
+        }
+        if (t == 0) {
+            atomicAdd(&a.ctl->stats[ST_P_TILES], 1ull);
+            atomicAdd(&a.ctl->stats[ST_P_CELLS], (unsigned long long)n);
+            atomicAdd(&a.ctl->stats[ST_P_KEPT], (unsigned long long)(base >= 0 ? total + 2 : 0));
+        }
+    }
+    if (t == 0) {
+        a.tiles[tile].position = out_position;
+        a.tiles[tile].tape = out_tape;
+        a.tiles[tile].next = -1;
+        atomicAdd(&a.ctl->stats[ST_I_TILES], 1ull);
+        atomicAdd(&a.ctl->stats[ST_I_CELLS], (unsigned long long)n);
+    }
+}
+
+////////////////////////////////////////////////////////////////////////////////
 // Post-mask + compaction (mask_filled_tiles #2, assign_next_nodes,
 // subdivide / copy_active_tiles bookkeeping; context.cu:471-551, :637-651)
 
@@ -521,9 +789,72 @@ k_upsample_filled(const int32_t* __restrict__ prev, int32_t* __restrict__ image,
 // Float pass (calculate_voxels / calculate_pixels + eval_voxels_f,
 // context.cu:707-964)
 
-template <int DIM>
+// Walks one tape for the two samples this lane holds; returns the result pair.
+// Clause semantics: context.cu:887-920.  There is no a*b+c shape in any clause,
+// so nothing here can be contracted; the _rn intrinsics just make that explicit.
+__device__ __forceinline__ float2 walk_float(const uint64_t* __restrict__ arena, int tape,
+                                             float2* __restrict__ slots, unsigned& cells)
+{
+    int pos = tape;
+    uint64_t d_next = arena[pos + 1];
+    uint64_t d;
+    for (;;) {
+        ++pos;
+        d = d_next;
+        const uint32_t w = uint32_t(d);
+        const uint32_t op = w & 0xff;
+        if (op == OP_END) break;
+        ++cells;
+        if (op == OP_JUMP) {
+            pos += int32_t(d >> 32);
+            d_next = arena[pos + 1];
+            continue;
+        }
+        d_next = arena[pos + 1];
+        const uint32_t i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
+        const float imm = __uint_as_float(uint32_t(d >> 32));
+        const float2 L = slots[i_lhs * 32];
+        const float2 R = slots[i_rhs * 32];
+        float2 o;
+        switch (op) {
+            case OP_SQUARE: o = make_float2(__fmul_rn(L.x, L.x), __fmul_rn(L.y, L.y)); break;
+            case OP_SQRT:   o = make_float2(sqrtf(L.x), sqrtf(L.y)); break;
+            case OP_NEG:    o = make_float2(-L.x, -L.y); break;
+            case OP_SIN:    o = make_float2(sinf(L.x), sinf(L.y)); break;
+            case OP_COS:    o = make_float2(cosf(L.x), cosf(L.y)); break;
+            case OP_ASIN:   o = make_float2(asinf(L.x), asinf(L.y)); break;
+            case OP_ACOS:   o = make_float2(acosf(L.x), acosf(L.y)); break;
+            case OP_ATAN:   o = make_float2(atanf(L.x), atanf(L.y)); break;
+            case OP_EXP:    o = make_float2(expf(L.x), expf(L.y)); break;
+            case OP_ABS:    o = make_float2(fabsf(L.x), fabsf(L.y)); break;
+            case OP_LOG:    o = make_float2(logf(L.x), logf(L.y)); break;
+            case OP_ADD_LI: o = make_float2(__fadd_rn(L.x, imm), __fadd_rn(L.y, imm)); break;
+            case OP_ADD_LR: o = make_float2(__fadd_rn(L.x, R.x), __fadd_rn(L.y, R.y)); break;
+            case OP_MUL_LI: o = make_float2(__fmul_rn(L.x, imm), __fmul_rn(L.y, imm)); break;
+            case OP_MUL_LR: o = make_float2(__fmul_rn(L.x, R.x), __fmul_rn(L.y, R.y)); break;
+            case OP_MIN_LI: o = make_float2(fminf(L.x, imm), fminf(L.y, imm)); break;
+            case OP_MIN_LR: o = make_float2(fminf(L.x, R.x), fminf(L.y, R.y)); break;
+            case OP_MAX_LI: o = make_float2(fmaxf(L.x, imm), fmaxf(L.y, imm)); break;
+            case OP_MAX_LR: o = make_float2(fmaxf(L.x, R.x), fmaxf(L.y, R.y)); break;
+            case OP_SUB_LI: o = make_float2(__fsub_rn(L.x, imm), __fsub_rn(L.y, imm)); break;
+            case OP_SUB_IR: o = make_float2(__fsub_rn(imm, R.x), __fsub_rn(imm, R.y)); break;
+            case OP_SUB_LR: o = make_float2(__fsub_rn(L.x, R.x), __fsub_rn(L.y, R.y)); break;
+            case OP_DIV_LI: o = make_float2(__fdiv_rn(L.x, imm), __fdiv_rn(L.y, imm)); break;
+            case OP_DIV_IR: o = make_float2(__fdiv_rn(imm, R.x), __fdiv_rn(imm, R.y)); break;
+            case OP_DIV_LR: o = make_float2(__fdiv_rn(L.x, R.x), __fdiv_rn(L.y, R.y)); break;
+            case OP_COPY_IMM: o = make_float2(imm, imm); break;
+            case OP_COPY_LHS: o = L; break;
+            case OP_COPY_RHS: o = R; break;
+            default: o = L; break;
+        }
+        slots[i_out * 32] = o;
+    }
+    return slots[((uint32_t(d) >> 8) & 0xff) * 32];
+}
+
+// 2D: one warp per surviving 8x8 tile, two pixels per lane (y and y + 4).
 __global__ void __launch_bounds__(kEvalThreads)
-k_eval_voxels(const EvalVoxelsArgs a, const typename MatOf<DIM>::type mat)
+k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 {
     extern __shared__ float2 s_slots[];
     const int lane = lane_id();
@@ -533,124 +864,85 @@ k_eval_voxels(const EvalVoxelsArgs a, const typename MatOf<DIM>::type mat)
     const uint32_t h = uint32_t(arena[0]);
     const int n_items = min(*a.n_tiles, a.tiles_cap);
     const uint32_t tps = a.tps;
+    const int size = tps * 8;
+    const float recip = 1.0f / float(tps * 8u);
+    const float* m = mat.d;
 
     for (;;) {
         const int item = warp_next(a.queue);
         if (item >= n_items) break;
         const TileNode tile = a.tiles[item];
         const int tx = tile.position % tps, ty = (tile.position / tps) % tps;
-
-        int px, py, pz = 0, img_a, img_b;
-        float2 X, Y, Z;
-        bool alive = true;
-        if (DIM == 3) {
-            const int tz = (tile.position / tps) / tps;
-            const int size = tps * 4;
-            px = tx * 4 + (lane & 3);
-            py = ty * 4 + ((lane >> 2) & 3);
-            pz = tz * 4 + (lane >> 4);          // second sample sits at pz + 2
-            img_a = img_b = px + py * size;
-            // This column already shows something at least as high (context.cu:852-864)
-            if (__ldcg(&a.image[img_a]) >= pz + 2) alive = false;
-            if (!__any_sync(kFull, alive)) continue;
-
-            const float recip = 1.0f / float(tps * 4u);
-            const float fx = sample_coord(px, recip), fy = sample_coord(py, recip);
-            const float fza = sample_coord(pz, recip), fzb = sample_coord(pz + 2, recip);
-            const float* m = mat.d;
-            const float wa = dot3(m[3], fx, m[7], fy, m[11], fza, m[15]);
-            const float wb = dot3(m[3], fx, m[7], fy, m[11], fzb, m[15]);
-            X = make_float2(dot3(m[0], fx, m[4], fy, m[8], fza, m[12]) / wa,
-                            dot3(m[0], fx, m[4], fy, m[8], fzb, m[12]) / wb);
-            Y = make_float2(dot3(m[1], fx, m[5], fy, m[9], fza, m[13]) / wa,
-                            dot3(m[1], fx, m[5], fy, m[9], fzb, m[13]) / wb);
-            Z = make_float2(dot3(m[2], fx, m[6], fy, m[10], fza, m[14]) / wa,
-                            dot3(m[2], fx, m[6], fy, m[10], fzb, m[14]) / wb);
-        } else {
-            const int size = tps * 8;
-            px = tx * 8 + (lane & 7);
-            py = ty * 8 + (lane >> 3);          // second sample sits at py + 4
-            img_a = px + py * size;
-            img_b = px + (py + 4) * size;
-            const float recip = 1.0f / float(tps * 8u);
-            const float fx = sample_coord(px, recip);
-            const float fya = sample_coord(py, recip), fyb = sample_coord(py + 4, recip);
-            const float* m = mat.d;
-            const float wa = dot2(m[2], fx, m[5], fya, m[8]);
-            const float wb = dot2(m[2], fx, m[5], fyb, m[8]);
-            X = make_float2(dot2(m[0], fx, m[3], fya, m[6]) / wa, dot2(m[0], fx, m[3], fyb, m[6]) / wb);
-            Y = make_float2(dot2(m[1], fx, m[4], fya, m[7]) / wa, dot2(m[1], fx, m[4], fyb, m[7]) / wb);
-            Z = make_float2(a.z, a.z);
-        }
-        slots[((h >> 8) & 0xff) * 32] = X;
-        slots[((h >> 16) & 0xff) * 32] = Y;
-        slots[(h >> 24) * 32] = Z;
-
-        int pos = tile.tape;
+        const int px = tx * 8 + (lane & 7);
+        const int py = ty * 8 + (lane >> 3);
+        const float fx = sample_coord(px, recip);
+        const float fya = sample_coord(py, recip), fyb = sample_coord(py + 4, recip);
+        const float wa = dot2(m[2], fx, m[5], fya, m[8]);
+        const float wb = dot2(m[2], fx, m[5], fyb, m[8]);
+        slots[((h >> 8) & 0xff) * 32] =
+            make_float2(dot2(m[0], fx, m[3], fya, m[6]) / wa, dot2(m[0], fx, m[3], fyb, m[6]) / wb);
+        slots[((h >> 16) & 0xff) * 32] =
+            make_float2(dot2(m[1], fx, m[4], fya, m[7]) / wa, dot2(m[1], fx, m[4], fyb, m[7]) / wb);
+        slots[(h >> 24) * 32] = make_float2(a.z, a.z);
         unsigned cells = 0;
-        uint64_t d_next = arena[pos + 1];
-        uint64_t d;
-        for (;;) {
-            ++pos;
-            d = d_next;
-            const uint32_t w = uint32_t(d);
-            const uint32_t op = w & 0xff;
-            if (op == OP_END) break;
-            ++cells;
-            if (op == OP_JUMP) {
-                pos += int32_t(d >> 32);
-                d_next = arena[pos + 1];
-                continue;
-            }
-            d_next = arena[pos + 1];
-            const uint32_t i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
-            const float imm = __uint_as_float(uint32_t(d >> 32));
-            const float2 L = slots[i_lhs * 32];
-            const float2 R = slots[i_rhs * 32];
-            float2 o;
-            switch (op) {   // context.cu:887-920; no a*b+c shapes here, so nothing contracts
-                case OP_SQUARE: o = make_float2(__fmul_rn(L.x, L.x), __fmul_rn(L.y, L.y)); break;
-                case OP_SQRT:   o = make_float2(sqrtf(L.x), sqrtf(L.y)); break;
-                case OP_NEG:    o = make_float2(-L.x, -L.y); break;
-                case OP_SIN:    o = make_float2(sinf(L.x), sinf(L.y)); break;
-                case OP_COS:    o = make_float2(cosf(L.x), cosf(L.y)); break;
-                case OP_ASIN:   o = make_float2(asinf(L.x), asinf(L.y)); break;
-                case OP_ACOS:   o = make_float2(acosf(L.x), acosf(L.y)); break;
-                case OP_ATAN:   o = make_float2(atanf(L.x), atanf(L.y)); break;
-                case OP_EXP:    o = make_float2(expf(L.x), expf(L.y)); break;
-                case OP_ABS:    o = make_float2(fabsf(L.x), fabsf(L.y)); break;
-                case OP_LOG:    o = make_float2(logf(L.x), logf(L.y)); break;
-                case OP_ADD_LI: o = make_float2(__fadd_rn(L.x, imm), __fadd_rn(L.y, imm)); break;
-                case OP_ADD_LR: o = make_float2(__fadd_rn(L.x, R.x), __fadd_rn(L.y, R.y)); break;
-                case OP_MUL_LI: o = make_float2(__fmul_rn(L.x, imm), __fmul_rn(L.y, imm)); break;
-                case OP_MUL_LR: o = make_float2(__fmul_rn(L.x, R.x), __fmul_rn(L.y, R.y)); break;
-                case OP_MIN_LI: o = make_float2(fminf(L.x, imm), fminf(L.y, imm)); break;
-                case OP_MIN_LR: o = make_float2(fminf(L.x, R.x), fminf(L.y, R.y)); break;
-                case OP_MAX_LI: o = make_float2(fmaxf(L.x, imm), fmaxf(L.y, imm)); break;
-                case OP_MAX_LR: o = make_float2(fmaxf(L.x, R.x), fmaxf(L.y, R.y)); break;
-                case OP_SUB_LI: o = make_float2(__fsub_rn(L.x, imm), __fsub_rn(L.y, imm)); break;
-                case OP_SUB_IR: o = make_float2(__fsub_rn(imm, R.x), __fsub_rn(imm, R.y)); break;
-                case OP_SUB_LR: o = make_float2(__fsub_rn(L.x, R.x), __fsub_rn(L.y, R.y)); break;
-                case OP_DIV_LI: o = make_float2(__fdiv_rn(L.x, imm), __fdiv_rn(L.y, imm)); break;
-                case OP_DIV_IR: o = make_float2(__fdiv_rn(imm, R.x), __fdiv_rn(imm, R.y)); break;
-                case OP_DIV_LR: o = make_float2(__fdiv_rn(L.x, R.x), __fdiv_rn(L.y, R.y)); break;
-                case OP_COPY_IMM: o = make_float2(imm, imm); break;
-                case OP_COPY_LHS: o = L; break;
-                case OP_COPY_RHS: o = R; break;
-                default: o = L; break;
-            }
-            slots[i_out * 32] = o;
+        const float2 r = walk_float(arena, tile.tape, slots, cells);
+        if (r.y < 0.0f) a.image[px + (py + 4) * size] = 1;      // context.cu:951-962
+        if (r.x < 0.0f) a.image[px + py * size] = 1;
+        if (lane == 0) {
+            atomicAdd(&a.ctl->stats[ST_F_TILES], 1ull);
+            atomicAdd(&a.ctl->stats[ST_F_CELLS], (unsigned long long)cells);
         }
-        const float2 r = slots[((uint32_t(d) >> 8) & 0xff) * 32];
+    }
+}
+
+// 3D: one warp per surviving 4x4x4 tile, two voxels per lane (z and z + 2).
+// Root tiles are issued highest-z first and children inherit that order, so the
+// list is roughly front-to-back and the per-lane early-out below (the
+// reference's, context.cu:852-864) culls most of what lies behind the surface.
+__global__ void __launch_bounds__(kEvalThreads)
+k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
+{
+    extern __shared__ float2 s_slots[];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    float2* const slots = s_slots + size_t(warp) * a.n_slots * 32 + lane;
+    const uint64_t* const arena = a.arena;
+    const uint32_t hdr = uint32_t(arena[0]);
+    const int n_items = min(*a.n_tiles, a.tiles_cap);
+    const uint32_t tps = a.tps;
+    const int size = tps * 4;
+    const float recip = 1.0f / float(tps * 4u);
+    const float* m = mat.d;
+
+    for (;;) {
+        const int item = warp_next(a.queue);
+        if (item >= n_items) break;
+        const TileNode tile = a.tiles[item];
+        const int tx = tile.position % tps, ty = (tile.position / tps) % tps, tz = (tile.position / tps) / tps;
+        const int px = tx * 4 + (lane & 3);
+        const int py = ty * 4 + ((lane >> 2) & 3);
+        const int pz = tz * 4 + (lane >> 4);            // second sample sits at pz + 2
+        int* const pix = &a.image[px + py * size];
+        // This column already shows something at least as high (context.cu:852-864)
+        const bool alive = __ldcg(pix) < pz + 2;
+        if (!__any_sync(kFull, alive)) continue;
+
+        const float fx = sample_coord(px, recip), fy = sample_coord(py, recip);
+        const float fza = sample_coord(pz, recip), fzb = sample_coord(pz + 2, recip);
+        const float wa = dot3(m[3], fx, m[7], fy, m[11], fza, m[15]);
+        const float wb = dot3(m[3], fx, m[7], fy, m[11], fzb, m[15]);
+        slots[((hdr >> 8) & 0xff) * 32] = make_float2(dot3(m[0], fx, m[4], fy, m[8], fza, m[12]) / wa,
+                                                      dot3(m[0], fx, m[4], fy, m[8], fzb, m[12]) / wb);
+        slots[((hdr >> 16) & 0xff) * 32] = make_float2(dot3(m[1], fx, m[5], fy, m[9], fza, m[13]) / wa,
+                                                       dot3(m[1], fx, m[5], fy, m[9], fzb, m[13]) / wb);
+        slots[(hdr >> 24) * 32] = make_float2(dot3(m[2], fx, m[6], fy, m[10], fza, m[14]) / wa,
+                                              dot3(m[2], fx, m[6], fy, m[10], fzb, m[14]) / wb);
+        unsigned cells = 0;
+        const float2 r = walk_float(arena, tile.tape, slots, cells);
         if (alive) {
-            if (DIM == 3) {
-                // The second sample is higher, so it wins when both are inside (context.cu:936-948)
-                if (r.y < 0.0f) atomicMax(&a.image[img_b], pz + 2);
-                else if (r.x < 0.0f) atomicMax(&a.image[img_a], pz);
-            } else {
-                if (r.y < 0.0f) a.image[img_b] = 1;
-                if (r.x < 0.0f) a.image[img_a] = 1;
-            }
+            // The higher sample wins when both are inside (context.cu:936-948)
+            if (r.y < 0.0f) atomicMax(pix, pz + 2);
+            else if (r.x < 0.0f) atomicMax(pix, pz);
         }
         if (lane == 0) {
             atomicAdd(&a.ctl->stats[ST_F_TILES], 1ull);
@@ -847,8 +1139,10 @@ void init_kernels(int max_smem_optin) {
     opt_in(k_eval_tiles<2, false>, max_smem_optin);
     opt_in(k_eval_tiles<3, true>, max_smem_optin);
     opt_in(k_eval_tiles<3, false>, max_smem_optin);
-    opt_in(k_eval_voxels<2>, max_smem_optin);
-    opt_in(k_eval_voxels<3>, max_smem_optin);
+    opt_in(k_eval_root<2>, max_smem_optin);
+    opt_in(k_eval_root<3>, max_smem_optin);
+    opt_in(k_eval_pixels, max_smem_optin);
+    opt_in(k_eval_voxels, max_smem_optin);
     opt_in(k_normals, max_smem_optin);
 }
 
@@ -869,6 +1163,14 @@ void launch_eval_tiles(int dim, bool root, const EvalTilesArgs& a, const void* m
     }
 }
 
+void launch_eval_root(int dim, const EvalRootArgs& a, const void* mat, cudaStream_t s) {
+    const int tiles_per_cta = kRootThreads / a.group;
+    const int grid = (a.count0 + tiles_per_cta - 1) / tiles_per_cta;
+    const size_t smem = size_t(tiles_per_cta) * a.smem_per_tile;
+    if (dim == 3) k_eval_root<3><<<grid, kRootThreads, smem, s>>>(a, *static_cast<const Mat4*>(mat));
+    else k_eval_root<2><<<grid, kRootThreads, smem, s>>>(a, *static_cast<const Mat3*>(mat));
+}
+
 void launch_rank_tiles(int dim, const RankArgs& a, int grid, cudaStream_t s) {
     if (dim == 3) k_rank_tiles<3><<<grid, 256, 0, s>>>(a);
     else k_rank_tiles<2><<<grid, 256, 0, s>>>(a);
@@ -879,13 +1181,14 @@ void launch_upsample_filled(int dim, const int32_t* prev, int32_t* image, int si
     else k_upsample_filled<2><<<grid, 256, 0, s>>>(prev, image, size);
 }
 
-void launch_eval_voxels(int dim, const EvalVoxelsArgs& a, const void* mat, int grid, cudaStream_t s) {
+void launch_eval_pixels(const EvalVoxelsArgs& a, const Mat3& mat, int grid, cudaStream_t s) {
     const size_t smem = size_t(kEvalWarps) * a.n_slots * 32 * sizeof(float2);
-    if (dim == 3) {
-        k_eval_voxels<3><<<grid, kEvalThreads, smem, s>>>(a, *static_cast<const Mat4*>(mat));
-    } else {
-        k_eval_voxels<2><<<grid, kEvalThreads, smem, s>>>(a, *static_cast<const Mat3*>(mat));
-    }
+    k_eval_pixels<<<grid, kEvalThreads, smem, s>>>(a, mat);
+}
+
+void launch_eval_voxels(const EvalVoxelsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
+    const size_t smem = size_t(kEvalWarps) * a.n_slots * 32 * sizeof(float2);
+    k_eval_voxels<<<grid, kEvalThreads, smem, s>>>(a, mat);
 }
 
 void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
@@ -913,8 +1216,8 @@ int occupancy_eval_tiles(int dim, bool root, int n_slots) {
 int occupancy_eval_voxels(int dim, int n_slots) {
     const size_t smem = size_t(kEvalWarps) * n_slots * 32 * sizeof(float2);
     int n = 0;
-    if (dim == 3) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_voxels<3>, kEvalThreads, smem); }
-    else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_voxels<2>, kEvalThreads, smem); }
+    if (dim == 3) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_voxels, kEvalThreads, smem); }
+    else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_pixels, kEvalThreads, smem); }
     return n;
 }
 

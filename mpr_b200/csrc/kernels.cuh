@@ -32,6 +32,37 @@ struct EvalTilesArgs {
     float z;                  // 2D only: the constant z
 };
 
+// One clause of a root tape in SSA / dependency-level order (built on the host per Tape).
+struct RootClause {
+    uint32_t op_idx;   // bits 0-7 opcode, bit 8 "verdict past the 4096-entry record", bits 12+ clause index
+    uint32_t lsrc;     // value id of the left operand  (0 none, 1..3 x/y/z, 3+i = clause i)
+    uint32_t rsrc;     // value id of the right operand
+    float imm;
+};
+
+constexpr int kRootThreads = 256;
+
+struct EvalRootArgs {
+    uint64_t* arena;
+    int32_t* tape_index;
+    int32_t arena_cap;
+    int32_t* image;           // level-0 filled image
+    TileNode* tiles;          // level-0 tile records (dense, index = position)
+    uint32_t tps;
+    int32_t count0;
+    int32_t row_begin;
+    int32_t row_end;
+    FrameCtl* ctl;
+    const RootClause* sched;  // clauses sorted by (dependency level, opcode)
+    const int32_t* level_start;   // n_levels + 1 offsets into sched
+    int32_t n_levels;
+    int32_t n_clauses;
+    int32_t result_v;         // value id of the tape's result
+    int32_t group;            // threads per tile: 32, 64, 128 or 256
+    int32_t smem_per_tile;    // bytes: values + verdicts + liveness + scratch
+    float z;
+};
+
 struct RankArgs {
     TileNode* tiles;          // this level's tile records
     int32_t tiles_cap;
@@ -79,9 +110,11 @@ struct NormalsArgs {
 void init_kernels(int max_smem_optin);
 void launch_begin_frame(FrameCtl* ctl, int32_t first_free, cudaStream_t s);
 void launch_eval_tiles(int dim, bool root, const EvalTilesArgs& a, const void* mat, int grid, cudaStream_t s);
+void launch_eval_root(int dim, const EvalRootArgs& a, const void* mat, cudaStream_t s);
 void launch_rank_tiles(int dim, const RankArgs& a, int grid, cudaStream_t s);
 void launch_upsample_filled(int dim, const int32_t* prev, int32_t* image, int size, int grid, cudaStream_t s);
-void launch_eval_voxels(int dim, const EvalVoxelsArgs& a, const void* mat, int grid, cudaStream_t s);
+void launch_eval_pixels(const EvalVoxelsArgs& a, const Mat3& mat, int grid, cudaStream_t s);
+void launch_eval_voxels(const EvalVoxelsArgs& a, const Mat4& mat, int grid, cudaStream_t s);
 void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_t s);
 
 // Resident CTAs per SM for a given slot count (sizes the persistent grids).
