@@ -71,8 +71,11 @@ cudaError_t managed_alloc(T** out, size_t count, int device) {
 }  // namespace
 
 struct mprb_tape {
-    uint64_t* cells = nullptr;   // managed
+    uint64_t* cells = nullptr;   // managed; the cells as given (Tape::data)
     int32_t length = 0;
+    uint64_t* chunked = nullptr; // device; the same tape in chunk-terminated layout (tape_stream.cuh)
+    int32_t n_chunked = 0;
+    std::vector<uint64_t> host_chunked;
     int32_t n_slots = 0;
     // Clause-parallel plan for the root level (see k_eval_root)
     RootClause* sched = nullptr;        // device
@@ -147,6 +150,31 @@ int validate_tape(const uint64_t* cells, int32_t n) {
     if (tape_num_slots(cells, n) > 128)
         return fail(MPRB_E_ARG, "tape uses more than 128 slots (the reference kernels hold 128)");
     return MPRB_OK;
+}
+
+// Contiguous tape -> chunk-terminated layout (see tape_stream.cuh).
+std::vector<uint64_t> chunk_layout(const uint64_t* cells, int32_t n) {
+    if (n <= kChunk) return std::vector<uint64_t>(cells, cells + n);
+    const int n_chunks = 1 + (n - 63 + 61) / 62;
+    std::vector<uint64_t> out(size_t(n_chunks) * kChunk, 0);
+    int last = 0;
+    for (int q = 0; q < n; ++q) {
+        int idx = q;
+        if (q >= kChunk - 1) {
+            const int r = q - (kChunk - 1);
+            idx = kChunk + (r / (kChunk - 2)) * kChunk + 1 + r % (kChunk - 2);
+        }
+        out[idx] = cells[q];
+        last = idx;
+    }
+    const uint64_t fwd = uint64_t(OP_JUMP) | (uint64_t(uint32_t(1)) << 32);
+    const uint64_t back = uint64_t(OP_JUMP) | (uint64_t(uint32_t(-1)) << 32);
+    for (int c = 0; c < n_chunks; ++c) {
+        if (c > 0) out[size_t(c) * kChunk] = back;
+        if (c + 1 < n_chunks) out[size_t(c) * kChunk + kChunk - 1] = fwd;
+    }
+    out.resize(size_t(last) + 1);
+    return out;
 }
 
 // Root tape -> SSA + dependency levels.  Value ids: 0 = none, 1..3 = x, y, z, 3+i = clause i.
@@ -241,14 +269,16 @@ struct Timer {
 
 // The frame proper.  `cells` may be a device/managed pointer (async D2D copy)
 // or a host pointer (async H2D copy through pinned staging).
-int render(mprb_ctx* c, int dim, const uint64_t* cells, int32_t n_cells, bool cells_on_host,
-           int n_slots, const float* matrix, float z, const mprb_tape* plan = nullptr)
+int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, const float* matrix, float z)
 {
-    if (!c) return fail(MPRB_E_ARG, "null context");
+    if (!c || !plan) return fail(MPRB_E_ARG, "null context or tape");
     const int S = c->size;
     cudaStream_t s = c->stream;
     MPRB_CUDA(cudaSetDevice(c->device));
-    if (n_cells >= c->arena_cells) return fail(MPRB_E_ARG, "tape longer than the arena");
+    const int32_t n_cells = plan->length;
+    const int32_t n_chunked = plan->n_chunked;
+    const int n_slots = plan->n_slots;
+    if (n_chunked + kChunk >= c->arena_cells) return fail(MPRB_E_ARG, "tape longer than the arena");
 
     const int tps0 = S / 64;
     const long long count0 = dim == 3 ? (long long)tps0 * tps0 * tps0 : (long long)tps0 * tps0;
@@ -276,22 +306,23 @@ int render(mprb_ctx* c, int dim, const uint64_t* cells, int32_t n_cells, bool ce
     Timer tm{c};
     tm.mark();
 
-    // Root tape to cell 0 of the arena (context.cu:1139-1142); pushed tapes start
-    // at the next 64-cell boundary so every chunk is 512-byte aligned.
-    const int32_t first_free = (n_cells + kChunk - 1) / kChunk * kChunk;
+    // Root tape to cell 0 of the arena (context.cu:1139-1142), in chunk-terminated layout;
+    // pushed tapes start at the next 64-cell boundary so every chunk is 512-byte aligned.
+    const int32_t first_free = (n_chunked + kChunk - 1) / kChunk * kChunk;
     launch_begin_frame(c->ctl, first_free, s);
     if (cells_on_host) {
-        if (c->stage_cells_cap < n_cells) {
+        // Host-buffer entry points pay the upload every frame: host cells -> pinned staging -> HBM.
+        if (c->stage_cells_cap < n_chunked) {
             if (c->stage_cells) cudaFreeHost(c->stage_cells);
             c->stage_cells = nullptr;
-            MPRB_CUDA(cudaMallocHost(&c->stage_cells, sizeof(uint64_t) * size_t(n_cells)));
-            c->stage_cells_cap = n_cells;
+            MPRB_CUDA(cudaMallocHost(&c->stage_cells, sizeof(uint64_t) * size_t(n_chunked)));
+            c->stage_cells_cap = n_chunked;
         }
-        memcpy(c->stage_cells, cells, sizeof(uint64_t) * size_t(n_cells));
-        MPRB_CUDA(cudaMemcpyAsync(c->arena, c->stage_cells, sizeof(uint64_t) * size_t(n_cells),
+        memcpy(c->stage_cells, plan->host_chunked.data(), sizeof(uint64_t) * size_t(n_chunked));
+        MPRB_CUDA(cudaMemcpyAsync(c->arena, c->stage_cells, sizeof(uint64_t) * size_t(n_chunked),
                                   cudaMemcpyHostToDevice, s));
     } else {
-        MPRB_CUDA(cudaMemcpyAsync(c->arena, cells, sizeof(uint64_t) * size_t(n_cells),
+        MPRB_CUDA(cudaMemcpyAsync(c->arena, plan->chunked, sizeof(uint64_t) * size_t(n_chunked),
                                   cudaMemcpyDeviceToDevice, s));
     }
     MPRB_CUDA(cudaMemsetAsync(c->filled[0], 0, sizeof(int32_t) * size_t(tps0) * tps0, s));
@@ -327,7 +358,7 @@ int render(mprb_ctx* c, int dim, const uint64_t* cells, int32_t n_cells, bool ce
         ea.level = l;
         ea.n_slots = n_slots;
         ea.z = z;
-        if (root && plan && plan->group > 0 && !c->serial_root) {
+        if (root && plan->group > 0 && !c->serial_root) {
             EvalRootArgs ra = {};
             ra.arena = c->arena;
             ra.tape_index = &c->ctl->tape_cursor;
@@ -339,6 +370,7 @@ int render(mprb_ctx* c, int dim, const uint64_t* cells, int32_t n_cells, bool ce
             ra.row_begin = c->row_begin;
             ra.row_end = c->row_end;
             ra.ctl = c->ctl;
+            ra.cells = plan->cells;
             ra.sched = plan->sched;
             ra.level_start = plan->level_start;
             ra.n_levels = plan->n_levels;
@@ -632,6 +664,16 @@ int mprb_tape_create(const uint64_t* host_cells, int32_t n_cells, mprb_tape** ou
     }
     t->length = n_cells;
     t->n_slots = tape_num_slots(host_cells, n_cells);
+    t->host_chunked = chunk_layout(host_cells, n_cells);
+    t->n_chunked = int32_t(t->host_chunked.size());
+    e = cudaMalloc(&t->chunked, sizeof(uint64_t) * t->host_chunked.size());
+    if (e == cudaSuccess)
+        e = cudaMemcpy(t->chunked, t->host_chunked.data(), sizeof(uint64_t) * t->host_chunked.size(),
+                       cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        mprb_tape_destroy(t);
+        return fail(MPRB_E_CUDA, "tape upload: %s", cudaGetErrorString(e));
+    }
     if (n_cells > 2 && n_cells - 2 < (1 << 20)) {
         const RootPlan plan = build_root_plan(host_cells, n_cells);
         const int n = n_cells - 2;
@@ -665,6 +707,7 @@ int mprb_tape_create(const uint64_t* host_cells, int32_t n_cells, mprb_tape** ou
 void mprb_tape_destroy(mprb_tape* t) {
     if (!t) return;
     if (t->cells) cudaFree(t->cells);
+    if (t->chunked) cudaFree(t->chunked);
     if (t->sched) cudaFree(t->sched);
     if (t->level_start) cudaFree(t->level_start);
     delete t;
@@ -676,13 +719,13 @@ int32_t mprb_tape_num_slots(const mprb_tape* t) { return t ? t->n_slots : 0; }
 
 int mprb_render2d(mprb_ctx* c, const mprb_tape* t, const float mat3[9], float z) {
     if (!c || !t || !mat3) return fail(MPRB_E_ARG, "null argument");
-    if (int e = render(c, 2, t->cells, t->length, false, t->n_slots, mat3, z, t)) return e;
+    if (int e = render(c, 2, t, false, mat3, z)) return e;
     return finish(c, 2);
 }
 
 int mprb_render3d(mprb_ctx* c, const mprb_tape* t, const float mat4[16]) {
     if (!c || !t || !mat4) return fail(MPRB_E_ARG, "null argument");
-    if (int e = render(c, 3, t->cells, t->length, false, t->n_slots, mat4, 0.0f, t)) return e;
+    if (int e = render(c, 3, t, false, mat4, 0.0f)) return e;
     return finish(c, 3);
 }
 
@@ -690,8 +733,9 @@ int mprb_render2d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
                        const float mat3[9], float z, int32_t* image_out) {
     if (!c || !mat3) return fail(MPRB_E_ARG, "null argument");
     if (int e = validate_tape(host_cells, n_cells)) return e;
-    if (int e = render(c, 2, host_cells, n_cells, true, tape_num_slots(host_cells, n_cells), mat3, z,
-                       host_plan_for(c, host_cells, n_cells))) return e;
+    const mprb_tape* t = host_plan_for(c, host_cells, n_cells);
+    if (!t) return MPRB_E_CUDA;
+    if (int e = render(c, 2, t, true, mat3, z)) return e;
     const size_t n = size_t(c->size) * c->size;
     if (image_out)
         MPRB_CUDA(cudaMemcpyAsync(image_out, c->filled[3], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -702,8 +746,9 @@ int mprb_render3d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
                        const float mat4[16], int32_t* depth_out, uint32_t* normals_out) {
     if (!c || !mat4) return fail(MPRB_E_ARG, "null argument");
     if (int e = validate_tape(host_cells, n_cells)) return e;
-    if (int e = render(c, 3, host_cells, n_cells, true, tape_num_slots(host_cells, n_cells), mat4, 0.0f,
-                       host_plan_for(c, host_cells, n_cells))) return e;
+    const mprb_tape* t = host_plan_for(c, host_cells, n_cells);
+    if (!t) return MPRB_E_CUDA;
+    if (int e = render(c, 3, t, true, mat4, 0.0f)) return e;
     const size_t n = size_t(c->size) * c->size;
     if (depth_out)
         MPRB_CUDA(cudaMemcpyAsync(depth_out, c->filled[3], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));

@@ -29,6 +29,7 @@
 #include "deriv.cuh"
 #include "ival.cuh"
 #include "kernels.cuh"
+#include "tape_stream.cuh"
 
 namespace mprb {
 
@@ -98,6 +99,29 @@ __device__ __forceinline__ float tile_edge(int p, float ftps) {
     return __fmul_rn(__fsub_rn(__fdiv_rn(float(p), ftps), 0.5f), 2.0f);
 }
 
+// Shared-memory slot rows addressed by 32-bit shared-space addresses: slot s of this lane
+// is at base + s * (32 lanes * sizeof value).  The clause word already holds each slot id in
+// its own byte, so `s * 256` is a mask (and a shift) away - no multiply, no 64-bit math.
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t off_out2(uint32_t w) { return w & 0xff00u; }            // out * 256
+__device__ __forceinline__ uint32_t off_lhs2(uint32_t w) { return (w >> 8) & 0xff00u; }     // lhs * 256
+__device__ __forceinline__ uint32_t off_rhs2(uint32_t w) { return (w >> 16) & 0xff00u; }    // rhs * 256
+
+// Bytes of dynamic shared memory a tape-walking CTA needs: slot rows + one chunk stream per warp.
+constexpr int kStreamStride = 640;   // kStreamBytes rounded up to a multiple of 128
+
 template <int N> struct MatOf;
 template <> struct MatOf<2> { typedef Mat3 type; };
 template <> struct MatOf<3> { typedef Mat4 type; };
@@ -111,11 +135,13 @@ template <int DIM, bool ROOT>
 __global__ void __launch_bounds__(kEvalThreads)
 k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
 {
-    extern __shared__ float2 s_slots[];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    // Slot s of this lane's tile lives at slots[s * 32].
-    float2* const slots = s_slots + size_t(warp) * a.n_slots * 32 + lane;
+    TapeStream ts;
+    ts.init(s_dyn + warp * kStreamStride, a.arena);
+    // Slot s of this lane's tile lives at slots + s * 256 (shared-space byte address).
+    const uint32_t slots = smem_addr(s_dyn + kEvalWarps * kStreamStride) + (warp * a.n_slots * 32 + lane) * 8;
 
     uint64_t* const arena = a.arena;
     uint32_t choices[kMaxChoices / 16];   // 2 bits per recorded min/max verdict
@@ -209,36 +235,39 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                 Z = iv(a.z, a.z);
             }
             const uint32_t h = uint32_t(root_hdr);
-            slots[((h >> 8) & 0xff) * 32] = X;
-            slots[((h >> 16) & 0xff) * 32] = Y;
-            slots[(h >> 24) * 32] = Z;
+            sts_f2(slots + off_out2(h), X);
+            sts_f2(slots + off_lhs2(h), Y);
+            sts_f2(slots + off_rhs2(h), Z);
         }
 
         // ---- forward walk (context.cu:223-287) -------------------------------------
-        int pos = tape;
+        // Every 64-cell chunk ends in a JUMP or the end cell (see tape_stream.cuh), so the hot
+        // path is a running shared-memory pointer; chunk switches happen only at JUMP cells.
+        ts.fetch(tape);
+        uint32_t cp = ts.buf + ((tape & (kChunk - 1)) << 3);
+        uint32_t seg = cp;         // where the current chunk segment started (for statistics)
         int n_choice = 0;          // warp-uniform: how many min/max clauses seen so far
         uint32_t cw = 0;           // verdict word under construction
         bool any_choice = false;
         unsigned cells = 0;
-        uint64_t d_next = arena[pos + 1];
-        uint64_t d;
+        uint2 d;
         for (;;) {
-            ++pos;
-            d = d_next;
-            const uint32_t w = uint32_t(d);
+            cp += 8;
+            d = lds_u2(cp);
+            const uint32_t w = d.x;
             const uint32_t op = w & 0xff;
-            if (op == OP_END) break;
-            ++cells;
-            if (op == OP_JUMP) {
-                pos += int32_t(d >> 32);
-                d_next = arena[pos + 1];
+            if (op <= OP_JUMP) {
+                cells += (cp - seg) >> 3;
+                if (op == OP_END) { --cells; break; }
+                const int t = ts.base + int((cp - ts.buf) >> 3) + int32_t(d.y);
+                ts.fetch(t);
+                cp = ts.buf + ((t & (kChunk - 1)) << 3);
+                seg = cp;
                 continue;
             }
-            d_next = arena[pos + 1];
-            const uint32_t i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
-            const float imm = __uint_as_float(uint32_t(d >> 32));
-            const ival L = slots[i_lhs * 32];
-            const ival R = slots[i_rhs * 32];
+            const float imm = __uint_as_float(d.y);
+            const ival L = lds_f2(slots + off_lhs2(w));
+            const ival R = lds_f2(slots + off_rhs2(w));
             ival o;
             int c = 0;
             switch (op) {
@@ -282,12 +311,12 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                 ++n_choice;
                 any_choice |= (c != 0);
             }
-            slots[i_out * 32] = o;
+            sts_f2(slots + off_out2(w), o);
         }
         if ((n_choice & 15) && n_choice < kMaxChoices) choices[n_choice >> 4] = cw;
-        const uint64_t end_cell = d;                       // {0, result slot}
-        const uint32_t i_result = (uint32_t(end_cell) >> 8) & 0xff;
-        const ival result = slots[i_result * 32];
+        const uint64_t end_cell = uint64_t(d.x) | (uint64_t(d.y) << 32);   // {0, result slot}
+        const uint32_t i_result = (d.x >> 8) & 0xff;
+        const ival result = lds_f2(slots + off_out2(d.x));
 
         // ---- classify (context.cu:289-321) -----------------------------------------
         int out_position = -1;
@@ -343,16 +372,23 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
             int ci = n_choice;
             int cw_index = -1;
             uint32_t cwb = 0;
+            seg = cp;
+            uint2 b;
             for (;;) {
-                d = arena[--pos];
-                const uint32_t w = uint32_t(d);
+                cp -= 8;
+                b = lds_u2(cp);
+                const uint32_t w = b.x;
                 const uint32_t op = w & 0xff;
-                if (op == OP_END) break;
-                ++bcells;
-                if (op == OP_JUMP) {
-                    pos += int32_t(d >> 32);
+                if (op <= OP_JUMP) {
+                    bcells += (seg - cp) >> 3;
+                    if (op == OP_END) { --bcells; break; }
+                    const int t = ts.base + int((cp - ts.buf) >> 3) + int32_t(b.y);
+                    ts.fetch(t);
+                    cp = ts.buf + ((t & (kChunk - 1)) << 3);
+                    seg = cp;
                     continue;
                 }
+                const uint64_t d64 = uint64_t(b.x) | (uint64_t(b.y) << 32);
                 const bool has_choice = (op >= OP_MIN_LI && op <= OP_MAX_LR);
                 int choice = 0;
                 if (has_choice) {
@@ -392,7 +428,7 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                         pushing = false;   // arena exhausted: keep the parent tape
                     } else {
                         live.reset(i_out);
-                        uint64_t e = d;
+                        uint64_t e = d64;
                         bool emit = true;
                         if (choice == 0) {
                             if (i_lhs) live.set(i_lhs);
@@ -400,14 +436,14 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                         } else if (choice == 1) {
                             live.set(i_lhs);
                             if (i_lhs == i_out) emit = false;
-                            else e = (d & ~0xffull) | OP_COPY_LHS;
+                            else e = (d64 & ~0xffull) | OP_COPY_LHS;
                         } else if (choice == 2) {
                             if (i_rhs) {
                                 live.set(i_rhs);
                                 if (i_rhs == i_out) emit = false;
-                                else e = (d & ~0xffull) | OP_COPY_RHS;
+                                else e = (d64 & ~0xffull) | OP_COPY_RHS;
                             } else {
-                                e = (d & ~0xffull) | OP_COPY_IMM;
+                                e = (d64 & ~0xffull) | OP_COPY_IMM;
                             }
                         }
                         if (emit) {
@@ -419,10 +455,10 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                     }
                 }
             }
-            // `d` is the header cell the walk stopped on; it goes in front.
+            // `b` is the header cell the walk stopped on; it goes in front.
             if (pushing) {
                 --o_off;
-                arena[o_idx + o_off] = d;
+                arena[o_idx + o_off] = uint64_t(b.x) | (uint64_t(b.y) << 32);
                 ++kept;
                 out_tape = o_idx + o_off;
             }
@@ -464,6 +500,14 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
 // group-wide prefix sum and written as one contiguous run (header, clauses, end
 // cell) - a valid tape in the reference's format that simply needs no JUMP.
 
+// Position of logical tape cell q in the chunk-terminated layout (see tape_stream.cuh); tapes
+// of at most 64 cells are stored as they are.
+__host__ __device__ __forceinline__ int chunked_index(int q, int n_logical) {
+    if (n_logical <= kChunk || q < kChunk - 1) return q;
+    const int r = q - (kChunk - 1);
+    return kChunk + (r / (kChunk - 2)) * kChunk + 1 + r % (kChunk - 2);
+}
+
 __device__ __forceinline__ void group_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -485,6 +529,7 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
     uint8_t* const A = C + nv;                              // liveness per value id
     int* const scratch = reinterpret_cast<int*>(mine + a.smem_per_tile - 64);
     uint64_t* const arena = a.arena;
+    const uint64_t* __restrict__ const cells = a.cells;     // the Tape's own contiguous cells
     const uint32_t tps = a.tps;
 
     int tile = blockIdx.x * (kRootThreads / G) + gid;
@@ -641,7 +686,7 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
         int kept = 0;
         for (int i = i_begin; i < i_end; ++i) {
             if (!A[3 + i]) continue;
-            const uint32_t w = uint32_t(arena[i]);
+            const uint32_t w = uint32_t(cells[i]);
             const uint32_t op = w & 0xff, i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
             const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[i] : 0;
             const bool dropped = (c == 1 && i_lhs == i_out) || (c == 2 && i_rhs != 0 && i_rhs == i_out);
@@ -663,8 +708,13 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
             if (wv < (t >> 5)) offset += s;
             total += s;
         }
+        // Logical cell q (0 = header, 1..total = clauses, total + 1 = end cell) goes to chunk
+        // layout position chunked_index(q): chunk 0 holds q = 0..62, every later chunk holds 62
+        // cells at offsets 1..62 between a back link (cell 0) and a forward link (cell 63).
+        const int n_logical = total + 2;
+        const int n_chunks = n_logical <= kChunk ? 1 : 1 + (n_logical - 63 + 61) / 62;
         if (t == 0) {
-            const int need = (total + 2 + kChunk - 1) / kChunk * kChunk;
+            const int need = n_chunks * kChunk;
             int base = -1;
             if (*(volatile int32_t*)a.tape_index < a.arena_cap) {
                 base = atomicAdd(a.tape_index, need);
@@ -675,10 +725,10 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
         group_sync(bar, G);
         const int base = scratch[3];
         if (base >= 0) {
-            int o = base + 1 + offset;
+            int q = 1 + offset;
             for (int i = i_begin; i < i_end; ++i) {
                 if (!A[3 + i]) continue;
-                uint64_t d = arena[i];
+                uint64_t d = cells[i];
                 const uint32_t w = uint32_t(d);
                 const uint32_t op = w & 0xff, i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
                 const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[i] : 0;
@@ -689,18 +739,23 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
                     if (i_rhs != 0 && i_rhs == i_out) continue;
                     d = (d & ~0xffull) | (i_rhs ? OP_COPY_RHS : OP_COPY_IMM);
                 }
-                arena[o++] = d;
+                arena[base + chunked_index(q, n_logical)] = d;
+                ++q;
             }
             if (t == 0) {
-                arena[base] = arena[0];                       // header
-                arena[base + total + 1] = arena[n + 1];       // end cell
+                arena[base] = cells[0];                                              // header
+                arena[base + chunked_index(total + 1, n_logical)] = cells[n + 1];    // end cell
+            }
+            for (int c = t; c < n_chunks; c += G) {                                  // chunk links
+                if (c > 0) arena[base + c * kChunk] = make_jump(-1);
+                if (c + 1 < n_chunks) arena[base + c * kChunk + kChunk - 1] = make_jump(1);
             }
             out_tape = base;
         }
         if (t == 0) {
             atomicAdd(&a.ctl->stats[ST_P_TILES], 1ull);
             atomicAdd(&a.ctl->stats[ST_P_CELLS], (unsigned long long)n);
-            atomicAdd(&a.ctl->stats[ST_P_KEPT], (unsigned long long)(base >= 0 ? total + 2 : 0));
+            atomicAdd(&a.ctl->stats[ST_P_KEPT], (unsigned long long)(base >= 0 ? total + 2 + 2 * (n_chunks - 1) : 0));
         }
     }
     if (t == 0) {
@@ -792,29 +847,30 @@ k_upsample_filled(const int32_t* __restrict__ prev, int32_t* __restrict__ image,
 // Walks one tape for the two samples this lane holds; returns the result pair.
 // Clause semantics: context.cu:887-920.  There is no a*b+c shape in any clause,
 // so nothing here can be contracted; the _rn intrinsics just make that explicit.
-__device__ __forceinline__ float2 walk_float(const uint64_t* __restrict__ arena, int tape,
-                                             float2* __restrict__ slots, unsigned& cells)
+// `slots` is this lane's shared-space base address (slot s at slots + s * 256).
+__device__ __forceinline__ float2 walk_float(TapeStream& ts, int tape, uint32_t slots, unsigned& cells)
 {
-    int pos = tape;
-    uint64_t d_next = arena[pos + 1];
-    uint64_t d;
+    ts.fetch(tape);
+    uint32_t cp = ts.buf + ((tape & (kChunk - 1)) << 3);
+    uint32_t seg = cp;
+    uint32_t w;
     for (;;) {
-        ++pos;
-        d = d_next;
-        const uint32_t w = uint32_t(d);
+        cp += 8;
+        const uint2 d = lds_u2(cp);
+        w = d.x;
         const uint32_t op = w & 0xff;
-        if (op == OP_END) break;
-        ++cells;
-        if (op == OP_JUMP) {
-            pos += int32_t(d >> 32);
-            d_next = arena[pos + 1];
+        if (op <= OP_JUMP) {
+            cells += (cp - seg) >> 3;
+            if (op == OP_END) { --cells; break; }
+            const int t = ts.base + int((cp - ts.buf) >> 3) + int32_t(d.y);
+            ts.fetch(t);
+            cp = ts.buf + ((t & (kChunk - 1)) << 3);
+            seg = cp;
             continue;
         }
-        d_next = arena[pos + 1];
-        const uint32_t i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
-        const float imm = __uint_as_float(uint32_t(d >> 32));
-        const float2 L = slots[i_lhs * 32];
-        const float2 R = slots[i_rhs * 32];
+        const float imm = __uint_as_float(d.y);
+        const float2 L = lds_f2(slots + off_lhs2(w));
+        const float2 R = lds_f2(slots + off_rhs2(w));
         float2 o;
         switch (op) {
             case OP_SQUARE: o = make_float2(__fmul_rn(L.x, L.x), __fmul_rn(L.y, L.y)); break;
@@ -847,19 +903,21 @@ __device__ __forceinline__ float2 walk_float(const uint64_t* __restrict__ arena,
             case OP_COPY_RHS: o = R; break;
             default: o = L; break;
         }
-        slots[i_out * 32] = o;
+        sts_f2(slots + off_out2(w), o);
     }
-    return slots[((uint32_t(d) >> 8) & 0xff) * 32];
+    return lds_f2(slots + off_out2(w));
 }
 
 // 2D: one warp per surviving 8x8 tile, two pixels per lane (y and y + 4).
 __global__ void __launch_bounds__(kEvalThreads)
 k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 {
-    extern __shared__ float2 s_slots[];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    float2* const slots = s_slots + size_t(warp) * a.n_slots * 32 + lane;
+    TapeStream ts;
+    ts.init(s_dyn + warp * kStreamStride, a.arena);
+    const uint32_t slots = smem_addr(s_dyn + kEvalWarps * kStreamStride) + (warp * a.n_slots * 32 + lane) * 8;
     const uint64_t* const arena = a.arena;
     const uint32_t h = uint32_t(arena[0]);
     const int n_items = min(*a.n_tiles, a.tiles_cap);
@@ -879,13 +937,13 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
         const float fya = sample_coord(py, recip), fyb = sample_coord(py + 4, recip);
         const float wa = dot2(m[2], fx, m[5], fya, m[8]);
         const float wb = dot2(m[2], fx, m[5], fyb, m[8]);
-        slots[((h >> 8) & 0xff) * 32] =
-            make_float2(dot2(m[0], fx, m[3], fya, m[6]) / wa, dot2(m[0], fx, m[3], fyb, m[6]) / wb);
-        slots[((h >> 16) & 0xff) * 32] =
-            make_float2(dot2(m[1], fx, m[4], fya, m[7]) / wa, dot2(m[1], fx, m[4], fyb, m[7]) / wb);
-        slots[(h >> 24) * 32] = make_float2(a.z, a.z);
+        sts_f2(slots + off_out2(h),
+               make_float2(dot2(m[0], fx, m[3], fya, m[6]) / wa, dot2(m[0], fx, m[3], fyb, m[6]) / wb));
+        sts_f2(slots + off_lhs2(h),
+               make_float2(dot2(m[1], fx, m[4], fya, m[7]) / wa, dot2(m[1], fx, m[4], fyb, m[7]) / wb));
+        sts_f2(slots + off_rhs2(h), make_float2(a.z, a.z));
         unsigned cells = 0;
-        const float2 r = walk_float(arena, tile.tape, slots, cells);
+        const float2 r = walk_float(ts, tile.tape, slots, cells);
         if (r.y < 0.0f) a.image[px + (py + 4) * size] = 1;      // context.cu:951-962
         if (r.x < 0.0f) a.image[px + py * size] = 1;
         if (lane == 0) {
@@ -902,10 +960,12 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 __global__ void __launch_bounds__(kEvalThreads)
 k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
 {
-    extern __shared__ float2 s_slots[];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    float2* const slots = s_slots + size_t(warp) * a.n_slots * 32 + lane;
+    TapeStream ts;
+    ts.init(s_dyn + warp * kStreamStride, a.arena);
+    const uint32_t slots = smem_addr(s_dyn + kEvalWarps * kStreamStride) + (warp * a.n_slots * 32 + lane) * 8;
     const uint64_t* const arena = a.arena;
     const uint32_t hdr = uint32_t(arena[0]);
     const int n_items = min(*a.n_tiles, a.tiles_cap);
@@ -931,14 +991,14 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
         const float fza = sample_coord(pz, recip), fzb = sample_coord(pz + 2, recip);
         const float wa = dot3(m[3], fx, m[7], fy, m[11], fza, m[15]);
         const float wb = dot3(m[3], fx, m[7], fy, m[11], fzb, m[15]);
-        slots[((hdr >> 8) & 0xff) * 32] = make_float2(dot3(m[0], fx, m[4], fy, m[8], fza, m[12]) / wa,
-                                                      dot3(m[0], fx, m[4], fy, m[8], fzb, m[12]) / wb);
-        slots[((hdr >> 16) & 0xff) * 32] = make_float2(dot3(m[1], fx, m[5], fy, m[9], fza, m[13]) / wa,
-                                                       dot3(m[1], fx, m[5], fy, m[9], fzb, m[13]) / wb);
-        slots[(hdr >> 24) * 32] = make_float2(dot3(m[2], fx, m[6], fy, m[10], fza, m[14]) / wa,
-                                              dot3(m[2], fx, m[6], fy, m[10], fzb, m[14]) / wb);
+        sts_f2(slots + off_out2(hdr), make_float2(dot3(m[0], fx, m[4], fy, m[8], fza, m[12]) / wa,
+                                                  dot3(m[0], fx, m[4], fy, m[8], fzb, m[12]) / wb));
+        sts_f2(slots + off_lhs2(hdr), make_float2(dot3(m[1], fx, m[5], fy, m[9], fza, m[13]) / wa,
+                                                  dot3(m[1], fx, m[5], fy, m[9], fzb, m[13]) / wb));
+        sts_f2(slots + off_rhs2(hdr), make_float2(dot3(m[2], fx, m[6], fy, m[10], fza, m[14]) / wa,
+                                                  dot3(m[2], fx, m[6], fy, m[10], fzb, m[14]) / wb));
         unsigned cells = 0;
-        const float2 r = walk_float(arena, tile.tape, slots, cells);
+        const float2 r = walk_float(ts, tile.tape, slots, cells);
         if (alive) {
             // The higher sample wins when both are inside (context.cu:936-948)
             if (r.y < 0.0f) atomicMax(pix, pz + 2);
@@ -1013,79 +1073,69 @@ k_normals(const NormalsArgs a, const Mat4 mat)
 
         dval result = dv_const(0.0f);
         unsigned my_cells = 0;
-        // Lanes that share a tape walk it together; distinct tapes take turns.
-        while (todo) {
-            const int leader = __ffs(todo) - 1;
-            const int cur = __shfl_sync(kFull, tape, leader);
-            const bool mine = (tape == cur);
-            todo &= ~__ballot_sync(kFull, mine);
-
-            // The reference binds x, then y, then z, and then overwrites the
-            // gradient components through the same slot indices; with distinct
-            // slots that is exactly these three stores.  (An unused axis maps
-            // to slot 0, which no clause reads.)
+        // Each lane walks ITS tile's tape.  Lanes whose pixels fall in the same 4^3 tile
+        // share a tape and stay in lockstep; lanes on different tapes sit at different
+        // cells, and only the opcode switch diverges (fetch, decode, operand loads and the
+        // store are the same instructions for everyone).  Slots are [slot][lane] float4
+        // rows, so per-lane slot indices are still bank-conflict free.
+        {
             slots[((h >> 8) & 0xff) * 32] = sx_;
             slots[((h >> 16) & 0xff) * 32] = sy_;
             slots[(h >> 24) * 32] = sz_;
-
-            int pos = cur;
-            unsigned cells = 0;
-            uint64_t d_next = arena[pos + 1];
-            uint64_t d;
-            for (;;) {
-                ++pos;
-                d = d_next;
-                const uint32_t w = uint32_t(d);
-                const uint32_t op = w & 0xff;
-                if (op == OP_END) break;
-                ++cells;
-                if (op == OP_JUMP) {
-                    pos += int32_t(d >> 32);
-                    d_next = arena[pos + 1];
-                    continue;
+            bool active = tape >= 0;
+            int pos = active ? tape : 0;
+            while (__any_sync(kFull, active)) {
+                if (active) {
+                    const uint64_t d = __ldg(&arena[++pos]);
+                    const uint32_t w = uint32_t(d);
+                    const uint32_t op = w & 0xff;
+                    if (op == OP_END) {
+                        result = slots[((w >> 8) & 0xff) * 32];
+                        active = false;
+                    } else if (op == OP_JUMP) {
+                        pos += int32_t(d >> 32);
+                        ++my_cells;
+                    } else {
+                        ++my_cells;
+                        const uint32_t i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
+                        const float imm = __uint_as_float(uint32_t(d >> 32));
+                        const dval L = slots[i_lhs * 32];
+                        const dval R = slots[i_rhs * 32];
+                        dval o;
+                        switch (op) {   // context.cu:1081-1114
+                            case OP_SQUARE: o = dv_mul(L, L); break;
+                            case OP_SQRT:   o = dv_sqrt(L); break;
+                            case OP_NEG:    o = dv_neg(L); break;
+                            case OP_SIN:    o = dv_sin(L); break;
+                            case OP_COS:    o = dv_cos(L); break;
+                            case OP_ASIN:   o = dv_asin(L); break;
+                            case OP_ACOS:   o = dv_acos(L); break;
+                            case OP_ATAN:   o = dv_atan(L); break;
+                            case OP_EXP:    o = dv_exp(L); break;
+                            case OP_ABS:    o = dv_abs(L); break;
+                            case OP_LOG:    o = dv_log(L); break;
+                            case OP_ADD_LI: o = dv_add(L, imm); break;
+                            case OP_ADD_LR: o = dv_add(L, R); break;
+                            case OP_MUL_LI: o = dv_mul(L, imm); break;
+                            case OP_MUL_LR: o = dv_mul(L, R); break;
+                            case OP_MIN_LI: o = dv_min(L, imm); break;
+                            case OP_MIN_LR: o = dv_min(L, R); break;
+                            case OP_MAX_LI: o = dv_max(L, imm); break;
+                            case OP_MAX_LR: o = dv_max(L, R); break;
+                            case OP_SUB_LI: o = dv_sub(L, imm); break;
+                            case OP_SUB_IR: o = dv_sub(imm, R); break;
+                            case OP_SUB_LR: o = dv_sub(L, R); break;
+                            case OP_DIV_LI: o = dv_div(L, imm); break;
+                            case OP_DIV_IR: o = dv_div(imm, R); break;
+                            case OP_DIV_LR: o = dv_div(L, R); break;
+                            case OP_COPY_IMM: o = dv_const(imm); break;
+                            case OP_COPY_LHS: o = L; break;
+                            case OP_COPY_RHS: o = R; break;
+                            default: o = L; break;
+                        }
+                        slots[i_out * 32] = o;
+                    }
                 }
-                d_next = arena[pos + 1];
-                const uint32_t i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
-                const float imm = __uint_as_float(uint32_t(d >> 32));
-                const dval L = slots[i_lhs * 32];
-                const dval R = slots[i_rhs * 32];
-                dval o;
-                switch (op) {   // context.cu:1081-1114
-                    case OP_SQUARE: o = dv_mul(L, L); break;
-                    case OP_SQRT:   o = dv_sqrt(L); break;
-                    case OP_NEG:    o = dv_neg(L); break;
-                    case OP_SIN:    o = dv_sin(L); break;
-                    case OP_COS:    o = dv_cos(L); break;
-                    case OP_ASIN:   o = dv_asin(L); break;
-                    case OP_ACOS:   o = dv_acos(L); break;
-                    case OP_ATAN:   o = dv_atan(L); break;
-                    case OP_EXP:    o = dv_exp(L); break;
-                    case OP_ABS:    o = dv_abs(L); break;
-                    case OP_LOG:    o = dv_log(L); break;
-                    case OP_ADD_LI: o = dv_add(L, imm); break;
-                    case OP_ADD_LR: o = dv_add(L, R); break;
-                    case OP_MUL_LI: o = dv_mul(L, imm); break;
-                    case OP_MUL_LR: o = dv_mul(L, R); break;
-                    case OP_MIN_LI: o = dv_min(L, imm); break;
-                    case OP_MIN_LR: o = dv_min(L, R); break;
-                    case OP_MAX_LI: o = dv_max(L, imm); break;
-                    case OP_MAX_LR: o = dv_max(L, R); break;
-                    case OP_SUB_LI: o = dv_sub(L, imm); break;
-                    case OP_SUB_IR: o = dv_sub(imm, R); break;
-                    case OP_SUB_LR: o = dv_sub(L, R); break;
-                    case OP_DIV_LI: o = dv_div(L, imm); break;
-                    case OP_DIV_IR: o = dv_div(imm, R); break;
-                    case OP_DIV_LR: o = dv_div(L, R); break;
-                    case OP_COPY_IMM: o = dv_const(imm); break;
-                    case OP_COPY_LHS: o = L; break;
-                    case OP_COPY_RHS: o = R; break;
-                    default: o = L; break;
-                }
-                slots[i_out * 32] = o;
-            }
-            if (mine) {
-                result = slots[((uint32_t(d) >> 8) & 0xff) * 32];
-                my_cells = cells;
             }
         }
 
@@ -1125,6 +1175,11 @@ __global__ void k_begin_frame(FrameCtl* ctl, int32_t first_free)
 // Launch wrappers
 
 // Opt every kernel in to the device's full dynamic shared memory once.
+// Dynamic shared memory of a tape-walking CTA: float2 slot rows + one chunk stream per warp.
+static size_t float_smem(int n_slots) {
+    return size_t(kEvalWarps) * (size_t(n_slots) * 32 * sizeof(float2) + kStreamStride);
+}
+
 // Also pin the L1/shared split to "all shared": occupancy here is bounded by shared memory,
 // and a device-wide cudaDeviceSetCacheConfig(PreferL1) made by other code in the process
 // (the reference's Context constructor does that, context.cpp:47-48) would otherwise shrink
@@ -1148,7 +1203,7 @@ void init_kernels(int max_smem_optin) {
 
 template <int DIM, bool ROOT>
 static void launch_eval_tiles_t(const EvalTilesArgs& a, const void* mat, int grid, cudaStream_t s) {
-    const size_t smem = size_t(kEvalWarps) * a.n_slots * 32 * sizeof(float2);
+    const size_t smem = float_smem(a.n_slots);
     auto kernel = k_eval_tiles<DIM, ROOT>;
     kernel<<<grid, kEvalThreads, smem, s>>>(a, *static_cast<const typename MatOf<DIM>::type*>(mat));
 }
@@ -1182,12 +1237,12 @@ void launch_upsample_filled(int dim, const int32_t* prev, int32_t* image, int si
 }
 
 void launch_eval_pixels(const EvalVoxelsArgs& a, const Mat3& mat, int grid, cudaStream_t s) {
-    const size_t smem = size_t(kEvalWarps) * a.n_slots * 32 * sizeof(float2);
+    const size_t smem = float_smem(a.n_slots);
     k_eval_pixels<<<grid, kEvalThreads, smem, s>>>(a, mat);
 }
 
 void launch_eval_voxels(const EvalVoxelsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
-    const size_t smem = size_t(kEvalWarps) * a.n_slots * 32 * sizeof(float2);
+    const size_t smem = float_smem(a.n_slots);
     k_eval_voxels<<<grid, kEvalThreads, smem, s>>>(a, mat);
 }
 
@@ -1201,7 +1256,7 @@ void launch_begin_frame(FrameCtl* ctl, int32_t first_free, cudaStream_t s) {
 }
 
 int occupancy_eval_tiles(int dim, bool root, int n_slots) {
-    const size_t smem = size_t(kEvalWarps) * n_slots * 32 * sizeof(float2);
+    const size_t smem = float_smem(n_slots);
     int n = 0;
     if (dim == 3) {
         if (root) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_tiles<3, true>, kEvalThreads, smem); }
@@ -1214,7 +1269,7 @@ int occupancy_eval_tiles(int dim, bool root, int n_slots) {
 }
 
 int occupancy_eval_voxels(int dim, int n_slots) {
-    const size_t smem = size_t(kEvalWarps) * n_slots * 32 * sizeof(float2);
+    const size_t smem = float_smem(n_slots);
     int n = 0;
     if (dim == 3) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_voxels, kEvalThreads, smem); }
     else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_pixels, kEvalThreads, smem); }

@@ -53,6 +53,7 @@ struct EvalRootArgs {
     int32_t row_begin;
     int32_t row_end;
     FrameCtl* ctl;
+    const uint64_t* cells;    // the Tape's contiguous cells (header, clauses, end cell)
     const RootClause* sched;  // clauses sorted by (dependency level, opcode)
     const int32_t* level_start;   // n_levels + 1 offsets into sched
     int32_t n_levels;
