@@ -119,6 +119,8 @@ int mprb_frame_stats_get(mprb_ctx* ctx, mprb_frame_stats* out);
 int mprb_tape_from_frep(const uint8_t* bytes, size_t n_bytes, int simplify,
                         uint64_t** cells_out, int32_t* n_cells_out, int32_t* n_slots_out);
 void mprb_free(void* p);
+/* Releases device / managed memory (cudaFree); counterpart of CUDA_FREE in inc/util.hpp. */
+void mprb_free_device(void* p);
 
 const char* mprb_last_error(void);
 const char* mprb_version(void);

@@ -76,7 +76,7 @@ EXPORTS = [
     "mprb_ctx_create", "mprb_ctx_destroy", "mprb_ctx_buffers", "mprb_ctx_set_timing",
     "mprb_tape_create", "mprb_tape_destroy", "mprb_tape_data", "mprb_tape_length",
     "mprb_tape_num_slots", "mprb_render2d", "mprb_render3d", "mprb_render2d_host",
-    "mprb_render3d_host", "mprb_frame_stats_get", "mprb_tape_from_frep", "mprb_free",
+    "mprb_render3d_host", "mprb_frame_stats_get", "mprb_tape_from_frep", "mprb_free", "mprb_free_device",
     "mprb_last_error", "mprb_version",
 ]
 
@@ -92,7 +92,7 @@ def lib():
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()); "
             "there is no CPU fallback for the render path")
-    L = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+    L = C.CDLL(str(LIB_PATH))   # RTLD_LOCAL: the C++ mpr:: symbols inside must not leak
     vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
     L.mprb_ctx_create.argtypes = [i32, C.POINTER(CtxOpts), C.POINTER(vp)]
     L.mprb_ctx_destroy.argtypes = [vp]

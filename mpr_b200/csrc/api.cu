@@ -784,5 +784,6 @@ int mprb_tape_from_frep(const uint8_t* bytes, size_t n_bytes, int simplify,
 }
 
 void mprb_free(void* p) { free(p); }
+void mprb_free_device(void* p) { if (p) cudaFree(p); }
 
 }  // extern "C"
