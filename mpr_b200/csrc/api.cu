@@ -357,6 +357,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         ea.queue = &c->ctl->queue[q++];
         ea.level = l;
         ea.n_slots = n_slots;
+        ea.n_rows = walk_rows(n_slots);
         ea.z = z;
         if (root && plan->group > 0 && !c->serial_root) {
             EvalRootArgs ra = {};
@@ -428,6 +429,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         va.ctl = c->ctl;
         va.queue = &c->ctl->queue[q++];
         va.n_slots = n_slots;
+        va.n_rows = walk_rows(n_slots);
         va.z = z;
         const int grid = c->sm_count * cached_occupancy(c, 1, dim, false, n_slots);
         if (dim == 2) launch_eval_pixels(va, m3, grid, s);

@@ -110,17 +110,47 @@ __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
 __device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
-__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ uint32_t off_out2(uint32_t w) { return w & 0xff00u; }            // out * 256
 __device__ __forceinline__ uint32_t off_lhs2(uint32_t w) { return (w >> 8) & 0xff00u; }     // lhs * 256
 __device__ __forceinline__ uint32_t off_rhs2(uint32_t w) { return (w >> 16) & 0xff00u; }    // rhs * 256
 
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Where one lane keeps its slot values.  `off` is always (slot or row) * 256, i.e. a masked
+// byte of the clause word.
+//   REMAP = false: rows of 32 lanes in shared memory, one per slot id - conflict free, no cache
+//                  misses; used while the root tape's slot count leaves enough occupancy.
+//   REMAP = true:  the stream has renamed ids to dense rows (tape_stream.cuh); the first
+//                  kRemapRows rows are shared-memory rows, later ones spill to local memory.
+template <bool REMAP> struct Slots2 {
+    uint32_t base;
+    uint32_t limit;      // REMAP: rows * 256 held in shared memory (rows >= kRemapRowsMin)
+    float2 loc[REMAP ? 128 - kRemapRowsMin : 1];
+    __device__ __forceinline__ float2 ld(uint32_t off) const {
+        if (REMAP && off >= limit) return loc[(off - limit) >> 8];
+        return lds_f2(base + off);
+    }
+    __device__ __forceinline__ void st(uint32_t off, float2 v) {
+        if (REMAP && off >= limit) loc[(off - limit) >> 8] = v;
+        else sts_f2(base + off, v);
+    }
+};
+// Normal pass: float4 values; LOCAL = true keeps them in per-thread local memory instead.
+template <bool LOCAL> struct Slots4 {
+    uint32_t base;
+    float4 loc[LOCAL ? 128 : 1];
+    __device__ __forceinline__ float4 ld(uint32_t off) const { return LOCAL ? loc[off >> 8] : lds_f4(base + (off << 1)); }
+    __device__ __forceinline__ void st(uint32_t off, float4 v) { if (LOCAL) loc[off >> 8] = v; else sts_f4(base + (off << 1), v); }
+};
+
 // Bytes of dynamic shared memory a tape-walking CTA needs: slot rows + one chunk stream per warp.
-constexpr int kStreamStride = 640;   // kStreamBytes rounded up to a multiple of 128
 
 template <int N> struct MatOf;
 template <> struct MatOf<2> { typedef Mat3 type; };
@@ -131,20 +161,25 @@ template <> struct MatOf<3> { typedef Mat4 type; };
 ////////////////////////////////////////////////////////////////////////////////
 // Interval pass
 
-template <int DIM, bool ROOT>
+template <int DIM, bool ROOT, bool REMAP>
 __global__ void __launch_bounds__(kEvalThreads)
 k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    TapeStream ts;
-    ts.init(s_dyn + warp * kStreamStride, a.arena);
-    // Slot s of this lane's tile lives at slots + s * 256 (shared-space byte address).
-    const uint32_t slots = smem_addr(s_dyn + kEvalWarps * kStreamStride) + (warp * a.n_slots * 32 + lane) * 8;
+    typedef TapeStream<REMAP> Stream;
+    Stream ts;
+    ts.init(s_dyn + warp * Stream::stride(), a.arena);
+    const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
+    Slots2<REMAP> slots;
+    slots.base = smem_addr(s_dyn + kEvalWarps * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
+    slots.limit = uint32_t(n_rows) * 256u;
 
     uint64_t* const arena = a.arena;
     uint32_t choices[kMaxChoices / 16];   // 2 bits per recorded min/max verdict
+    // statistics accumulate per warp and are flushed once (one atomic per counter per warp)
+    unsigned long long st_tiles = 0, st_cells = 0, st_ptiles = 0, st_pcells = 0, st_kept = 0;
 
     const int n_items = ROOT ? (a.count0 + 31) / 32 : 2 * min(*a.n_parents, a.tiles_cap / 64);
     const uint32_t tps = a.tps;
@@ -206,6 +241,7 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
         }
 
         // ---- tile box -> transformed intervals (context.cu:78-159) ---------------
+        const uint32_t h = ts.begin_tape(uint32_t(root_hdr));   // axis slots (renamed to rows if REMAP)
         {
             const float ftps = float(tps);
             const ival ix = iv(tile_edge(sx, ftps), tile_edge(sx + 1, ftps));
@@ -234,17 +270,16 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                 Y = iv_div(r[1], r[2]);
                 Z = iv(a.z, a.z);
             }
-            const uint32_t h = uint32_t(root_hdr);
-            sts_f2(slots + off_out2(h), X);
-            sts_f2(slots + off_lhs2(h), Y);
-            sts_f2(slots + off_rhs2(h), Z);
+            slots.st(off_out2(h), X);
+            slots.st(off_lhs2(h), Y);
+            slots.st(off_rhs2(h), Z);
         }
 
         // ---- forward walk (context.cu:223-287) -------------------------------------
         // Every 64-cell chunk ends in a JUMP or the end cell (see tape_stream.cuh), so the hot
         // path is a running shared-memory pointer; chunk switches happen only at JUMP cells.
         ts.fetch(tape);
-        uint32_t cp = ts.buf + ((tape & (kChunk - 1)) << 3);
+        uint32_t cp = ts.rd + ((tape & (kChunk - 1)) << 3);
         uint32_t seg = cp;         // where the current chunk segment started (for statistics)
         int n_choice = 0;          // warp-uniform: how many min/max clauses seen so far
         uint32_t cw = 0;           // verdict word under construction
@@ -259,15 +294,15 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
             if (op <= OP_JUMP) {
                 cells += (cp - seg) >> 3;
                 if (op == OP_END) { --cells; break; }
-                const int t = ts.base + int((cp - ts.buf) >> 3) + int32_t(d.y);
+                const int t = ts.base + int((cp - ts.rd) >> 3) + int32_t(d.y);
                 ts.fetch(t);
-                cp = ts.buf + ((t & (kChunk - 1)) << 3);
+                cp = ts.rd + ((t & (kChunk - 1)) << 3);
                 seg = cp;
                 continue;
             }
             const float imm = __uint_as_float(d.y);
-            const ival L = lds_f2(slots + off_lhs2(w));
-            const ival R = lds_f2(slots + off_rhs2(w));
+            const ival L = slots.ld(off_lhs2(w));
+            const ival R = slots.ld(off_rhs2(w));
             ival o;
             int c = 0;
             switch (op) {
@@ -311,12 +346,13 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                 ++n_choice;
                 any_choice |= (c != 0);
             }
-            sts_f2(slots + off_out2(w), o);
+            slots.st(off_out2(w), o);
         }
         if ((n_choice & 15) && n_choice < kMaxChoices) choices[n_choice >> 4] = cw;
-        const uint64_t end_cell = uint64_t(d.x) | (uint64_t(d.y) << 32);   // {0, result slot}
+        const uint2 end_raw = lds_u2(ts.buf + (cp - ts.rd));              // as stored in the arena
+        const uint64_t end_cell = uint64_t(end_raw.x) | (uint64_t(end_raw.y) << 32);   // {0, result slot}
         const uint32_t i_result = (d.x >> 8) & 0xff;
-        const ival result = lds_f2(slots + off_out2(d.x));
+        const ival result = slots.ld(off_out2(d.x));
 
         // ---- classify (context.cu:289-321) -----------------------------------------
         int out_position = -1;
@@ -339,10 +375,8 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
         // ---- statistics ----------------------------------------------------------------
         {
             const unsigned n_alive = __popc(__ballot_sync(kFull, alive));
-            if (lane == 0) {
-                atomicAdd(&a.ctl->stats[ST_I_TILES + a.level], (unsigned long long)n_alive);
-                atomicAdd(&a.ctl->stats[ST_I_CELLS + a.level], (unsigned long long)n_alive * cells);
-            }
+            st_tiles += n_alive;
+            st_cells += (unsigned long long)n_alive * cells;
         }
 
         // ---- tape push: backward mark & sweep (context.cu:323-458) ---------------------
@@ -382,13 +416,12 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                 if (op <= OP_JUMP) {
                     bcells += (seg - cp) >> 3;
                     if (op == OP_END) { --bcells; break; }
-                    const int t = ts.base + int((cp - ts.buf) >> 3) + int32_t(b.y);
-                    ts.fetch(t);
-                    cp = ts.buf + ((t & (kChunk - 1)) << 3);
+                    const int t = ts.base + int((cp - ts.rd) >> 3) + int32_t(b.y);
+                    ts.fetch_back(t);
+                    cp = ts.rd + ((t & (kChunk - 1)) << 3);
                     seg = cp;
                     continue;
                 }
-                const uint64_t d64 = uint64_t(b.x) | (uint64_t(b.y) << 32);
                 const bool has_choice = (op >= OP_MIN_LI && op <= OP_MAX_LR);
                 int choice = 0;
                 if (has_choice) {
@@ -428,6 +461,8 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                         pushing = false;   // arena exhausted: keep the parent tape
                     } else {
                         live.reset(i_out);
+                        const uint2 raw = lds_u2(ts.buf + (cp - ts.rd));     // cell as stored (ids, not rows)
+                        const uint64_t d64 = uint64_t(raw.x) | (uint64_t(raw.y) << 32);
                         uint64_t e = d64;
                         bool emit = true;
                         if (choice == 0) {
@@ -455,21 +490,19 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                     }
                 }
             }
-            // `b` is the header cell the walk stopped on; it goes in front.
+            // The walk stopped on the header cell; it goes in front (raw copy).
             if (pushing) {
                 --o_off;
-                arena[o_idx + o_off] = uint64_t(b.x) | (uint64_t(b.y) << 32);
+                const uint2 hraw = lds_u2(ts.buf + (cp - ts.rd));
+                arena[o_idx + o_off] = uint64_t(hraw.x) | (uint64_t(hraw.y) << 32);
                 ++kept;
                 out_tape = o_idx + o_off;
             }
             {
                 const unsigned n_push = __popc(__ballot_sync(kFull, pushed0));
-                const unsigned long long k_sum = warp_sum(pushed0 ? kept : 0u);
-                if (lane == 0) {
-                    atomicAdd(&a.ctl->stats[ST_P_TILES + a.level], (unsigned long long)n_push);
-                    atomicAdd(&a.ctl->stats[ST_P_CELLS + a.level], (unsigned long long)n_push * bcells);
-                    atomicAdd(&a.ctl->stats[ST_P_KEPT + a.level], k_sum);
-                }
+                st_ptiles += n_push;
+                st_pcells += (unsigned long long)n_push * bcells;
+                st_kept += warp_sum(pushed0 ? kept : 0u);
             }
         }
 
@@ -477,6 +510,15 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
             a.tiles[tile_index].position = out_position;
             a.tiles[tile_index].tape = out_tape;
             a.tiles[tile_index].next = -1;
+        }
+    }
+    if (lane == 0 && st_tiles) {
+        atomicAdd(&a.ctl->stats[ST_I_TILES + a.level], st_tiles);
+        atomicAdd(&a.ctl->stats[ST_I_CELLS + a.level], st_cells);
+        if (st_ptiles) {
+            atomicAdd(&a.ctl->stats[ST_P_TILES + a.level], st_ptiles);
+            atomicAdd(&a.ctl->stats[ST_P_CELLS + a.level], st_pcells);
+            atomicAdd(&a.ctl->stats[ST_P_KEPT + a.level], st_kept);
         }
     }
 }
@@ -848,10 +890,11 @@ k_upsample_filled(const int32_t* __restrict__ prev, int32_t* __restrict__ image,
 // Clause semantics: context.cu:887-920.  There is no a*b+c shape in any clause,
 // so nothing here can be contracted; the _rn intrinsics just make that explicit.
 // `slots` is this lane's shared-space base address (slot s at slots + s * 256).
-__device__ __forceinline__ float2 walk_float(TapeStream& ts, int tape, uint32_t slots, unsigned& cells)
+template <bool REMAP>
+__device__ __forceinline__ float2 walk_float(TapeStream<REMAP>& ts, int tape, Slots2<REMAP>& slots, unsigned& cells)
 {
     ts.fetch(tape);
-    uint32_t cp = ts.buf + ((tape & (kChunk - 1)) << 3);
+    uint32_t cp = ts.rd + ((tape & (kChunk - 1)) << 3);
     uint32_t seg = cp;
     uint32_t w;
     for (;;) {
@@ -862,15 +905,15 @@ __device__ __forceinline__ float2 walk_float(TapeStream& ts, int tape, uint32_t 
         if (op <= OP_JUMP) {
             cells += (cp - seg) >> 3;
             if (op == OP_END) { --cells; break; }
-            const int t = ts.base + int((cp - ts.buf) >> 3) + int32_t(d.y);
+            const int t = ts.base + int((cp - ts.rd) >> 3) + int32_t(d.y);
             ts.fetch(t);
-            cp = ts.buf + ((t & (kChunk - 1)) << 3);
+            cp = ts.rd + ((t & (kChunk - 1)) << 3);
             seg = cp;
             continue;
         }
         const float imm = __uint_as_float(d.y);
-        const float2 L = lds_f2(slots + off_lhs2(w));
-        const float2 R = lds_f2(slots + off_rhs2(w));
+        const float2 L = slots.ld(off_lhs2(w));
+        const float2 R = slots.ld(off_rhs2(w));
         float2 o;
         switch (op) {
             case OP_SQUARE: o = make_float2(__fmul_rn(L.x, L.x), __fmul_rn(L.y, L.y)); break;
@@ -903,23 +946,29 @@ __device__ __forceinline__ float2 walk_float(TapeStream& ts, int tape, uint32_t 
             case OP_COPY_RHS: o = R; break;
             default: o = L; break;
         }
-        sts_f2(slots + off_out2(w), o);
+        slots.st(off_out2(w), o);
     }
-    return lds_f2(slots + off_out2(w));
+    return slots.ld(off_out2(w));
 }
 
 // 2D: one warp per surviving 8x8 tile, two pixels per lane (y and y + 4).
+template <bool REMAP>
 __global__ void __launch_bounds__(kEvalThreads)
 k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    TapeStream ts;
-    ts.init(s_dyn + warp * kStreamStride, a.arena);
-    const uint32_t slots = smem_addr(s_dyn + kEvalWarps * kStreamStride) + (warp * a.n_slots * 32 + lane) * 8;
+    typedef TapeStream<REMAP> Stream;
+    Stream ts;
+    ts.init(s_dyn + warp * Stream::stride(), a.arena);
+    const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
+    Slots2<REMAP> slots;
+    slots.base = smem_addr(s_dyn + kEvalWarps * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
+    slots.limit = uint32_t(n_rows) * 256u;
     const uint64_t* const arena = a.arena;
-    const uint32_t h = uint32_t(arena[0]);
+    unsigned long long st_tiles = 0, st_cells = 0;
+    const uint32_t root_hdr = uint32_t(arena[0]);
     const int n_items = min(*a.n_tiles, a.tiles_cap);
     const uint32_t tps = a.tps;
     const int size = tps * 8;
@@ -937,19 +986,22 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
         const float fya = sample_coord(py, recip), fyb = sample_coord(py + 4, recip);
         const float wa = dot2(m[2], fx, m[5], fya, m[8]);
         const float wb = dot2(m[2], fx, m[5], fyb, m[8]);
-        sts_f2(slots + off_out2(h),
-               make_float2(dot2(m[0], fx, m[3], fya, m[6]) / wa, dot2(m[0], fx, m[3], fyb, m[6]) / wb));
-        sts_f2(slots + off_lhs2(h),
-               make_float2(dot2(m[1], fx, m[4], fya, m[7]) / wa, dot2(m[1], fx, m[4], fyb, m[7]) / wb));
-        sts_f2(slots + off_rhs2(h), make_float2(a.z, a.z));
+        const uint32_t h = ts.begin_tape(root_hdr);
+        slots.st(off_out2(h),
+                 make_float2(dot2(m[0], fx, m[3], fya, m[6]) / wa, dot2(m[0], fx, m[3], fyb, m[6]) / wb));
+        slots.st(off_lhs2(h),
+                 make_float2(dot2(m[1], fx, m[4], fya, m[7]) / wa, dot2(m[1], fx, m[4], fyb, m[7]) / wb));
+        slots.st(off_rhs2(h), make_float2(a.z, a.z));
         unsigned cells = 0;
         const float2 r = walk_float(ts, tile.tape, slots, cells);
         if (r.y < 0.0f) a.image[px + (py + 4) * size] = 1;      // context.cu:951-962
         if (r.x < 0.0f) a.image[px + py * size] = 1;
-        if (lane == 0) {
-            atomicAdd(&a.ctl->stats[ST_F_TILES], 1ull);
-            atomicAdd(&a.ctl->stats[ST_F_CELLS], (unsigned long long)cells);
-        }
+        st_tiles += 1;
+        st_cells += cells;
+    }
+    if (lane == 0 && st_tiles) {
+        atomicAdd(&a.ctl->stats[ST_F_TILES], st_tiles);
+        atomicAdd(&a.ctl->stats[ST_F_CELLS], st_cells);
     }
 }
 
@@ -957,17 +1009,23 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 // Root tiles are issued highest-z first and children inherit that order, so the
 // list is roughly front-to-back and the per-lane early-out below (the
 // reference's, context.cu:852-864) culls most of what lies behind the surface.
+template <bool REMAP>
 __global__ void __launch_bounds__(kEvalThreads)
 k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    TapeStream ts;
-    ts.init(s_dyn + warp * kStreamStride, a.arena);
-    const uint32_t slots = smem_addr(s_dyn + kEvalWarps * kStreamStride) + (warp * a.n_slots * 32 + lane) * 8;
+    typedef TapeStream<REMAP> Stream;
+    Stream ts;
+    ts.init(s_dyn + warp * Stream::stride(), a.arena);
+    const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
+    Slots2<REMAP> slots;
+    slots.base = smem_addr(s_dyn + kEvalWarps * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
+    slots.limit = uint32_t(n_rows) * 256u;
     const uint64_t* const arena = a.arena;
-    const uint32_t hdr = uint32_t(arena[0]);
+    unsigned long long st_tiles = 0, st_cells = 0;
+    const uint32_t root_hdr = uint32_t(arena[0]);
     const int n_items = min(*a.n_tiles, a.tiles_cap);
     const uint32_t tps = a.tps;
     const int size = tps * 4;
@@ -991,12 +1049,13 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
         const float fza = sample_coord(pz, recip), fzb = sample_coord(pz + 2, recip);
         const float wa = dot3(m[3], fx, m[7], fy, m[11], fza, m[15]);
         const float wb = dot3(m[3], fx, m[7], fy, m[11], fzb, m[15]);
-        sts_f2(slots + off_out2(hdr), make_float2(dot3(m[0], fx, m[4], fy, m[8], fza, m[12]) / wa,
-                                                  dot3(m[0], fx, m[4], fy, m[8], fzb, m[12]) / wb));
-        sts_f2(slots + off_lhs2(hdr), make_float2(dot3(m[1], fx, m[5], fy, m[9], fza, m[13]) / wa,
-                                                  dot3(m[1], fx, m[5], fy, m[9], fzb, m[13]) / wb));
-        sts_f2(slots + off_rhs2(hdr), make_float2(dot3(m[2], fx, m[6], fy, m[10], fza, m[14]) / wa,
-                                                  dot3(m[2], fx, m[6], fy, m[10], fzb, m[14]) / wb));
+        const uint32_t hdr = ts.begin_tape(root_hdr);
+        slots.st(off_out2(hdr), make_float2(dot3(m[0], fx, m[4], fy, m[8], fza, m[12]) / wa,
+                                            dot3(m[0], fx, m[4], fy, m[8], fzb, m[12]) / wb));
+        slots.st(off_lhs2(hdr), make_float2(dot3(m[1], fx, m[5], fy, m[9], fza, m[13]) / wa,
+                                            dot3(m[1], fx, m[5], fy, m[9], fzb, m[13]) / wb));
+        slots.st(off_rhs2(hdr), make_float2(dot3(m[2], fx, m[6], fy, m[10], fza, m[14]) / wa,
+                                            dot3(m[2], fx, m[6], fy, m[10], fzb, m[14]) / wb));
         unsigned cells = 0;
         const float2 r = walk_float(ts, tile.tape, slots, cells);
         if (alive) {
@@ -1004,23 +1063,28 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
             if (r.y < 0.0f) atomicMax(pix, pz + 2);
             else if (r.x < 0.0f) atomicMax(pix, pz);
         }
-        if (lane == 0) {
-            atomicAdd(&a.ctl->stats[ST_F_TILES], 1ull);
-            atomicAdd(&a.ctl->stats[ST_F_CELLS], (unsigned long long)cells);
-        }
+        st_tiles += 1;
+        st_cells += cells;
+    }
+    if (lane == 0 && st_tiles) {
+        atomicAdd(&a.ctl->stats[ST_F_TILES], st_tiles);
+        atomicAdd(&a.ctl->stats[ST_F_CELLS], st_cells);
     }
 }
 
 ////////////////////////////////////////////////////////////////////////////////
 // Normal pass (eval_pixels_d, context.cu:978-1132)
 
+template <bool LOCAL>
 __global__ void __launch_bounds__(kEvalThreads)
 k_normals(const NormalsArgs a, const Mat4 mat)
 {
-    extern __shared__ float4 s_dslots[];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    float4* const slots = s_dslots + size_t(warp) * a.n_slots * 32 + lane;
+    Slots4<LOCAL> slots;
+    slots.base = smem_addr(s_dyn) + (warp * a.n_slots * 32 + lane) * 16;
+    unsigned long long st_px = 0, st_cells = 0;
     const uint64_t* const arena = a.arena;
     const uint32_t h = uint32_t(arena[0]);
     const int size = a.size;
@@ -1079,9 +1143,9 @@ k_normals(const NormalsArgs a, const Mat4 mat)
         // store are the same instructions for everyone).  Slots are [slot][lane] float4
         // rows, so per-lane slot indices are still bank-conflict free.
         {
-            slots[((h >> 8) & 0xff) * 32] = sx_;
-            slots[((h >> 16) & 0xff) * 32] = sy_;
-            slots[(h >> 24) * 32] = sz_;
+            slots.st(off_out2(h), sx_);
+            slots.st(off_lhs2(h), sy_);
+            slots.st(off_rhs2(h), sz_);
             bool active = tape >= 0;
             int pos = active ? tape : 0;
             while (__any_sync(kFull, active)) {
@@ -1090,17 +1154,16 @@ k_normals(const NormalsArgs a, const Mat4 mat)
                     const uint32_t w = uint32_t(d);
                     const uint32_t op = w & 0xff;
                     if (op == OP_END) {
-                        result = slots[((w >> 8) & 0xff) * 32];
+                        result = slots.ld(off_out2(w));
                         active = false;
                     } else if (op == OP_JUMP) {
                         pos += int32_t(d >> 32);
                         ++my_cells;
                     } else {
                         ++my_cells;
-                        const uint32_t i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
                         const float imm = __uint_as_float(uint32_t(d >> 32));
-                        const dval L = slots[i_lhs * 32];
-                        const dval R = slots[i_rhs * 32];
+                        const dval L = slots.ld(off_lhs2(w));
+                        const dval R = slots.ld(off_rhs2(w));
                         dval o;
                         switch (op) {   // context.cu:1081-1114
                             case OP_SQUARE: o = dv_mul(L, L); break;
@@ -1133,7 +1196,7 @@ k_normals(const NormalsArgs a, const Mat4 mat)
                             case OP_COPY_RHS: o = R; break;
                             default: o = L; break;
                         }
-                        slots[i_out * 32] = o;
+                        slots.st(off_out2(w), o);
                     }
                 }
             }
@@ -1149,13 +1212,13 @@ k_normals(const NormalsArgs a, const Mat4 mat)
             a.normals[pxy] = (0xFFu << 24) | (uint32_t(bz) << 16) | (uint32_t(by) << 8) | bx;
         }
         {
-            const unsigned n_px = __popc(__ballot_sync(kFull, tape >= 0));
-            const unsigned long long c_sum = warp_sum(tape >= 0 ? my_cells : 0u);
-            if (lane == 0) {
-                atomicAdd(&a.ctl->stats[ST_N_PIXELS], (unsigned long long)n_px);
-                atomicAdd(&a.ctl->stats[ST_N_CELLS], c_sum);
-            }
+            st_px += __popc(__ballot_sync(kFull, tape >= 0));
+            st_cells += warp_sum(tape >= 0 ? my_cells : 0u);
         }
+    }
+    if (lane == 0 && st_px) {
+        atomicAdd(&a.ctl->stats[ST_N_PIXELS], st_px);
+        atomicAdd(&a.ctl->stats[ST_N_CELLS], st_cells);
     }
 }
 
@@ -1175,37 +1238,71 @@ __global__ void k_begin_frame(FrameCtl* ctl, int32_t first_free)
 // Launch wrappers
 
 // Opt every kernel in to the device's full dynamic shared memory once.
-// Dynamic shared memory of a tape-walking CTA: float2 slot rows + one chunk stream per warp.
-static size_t float_smem(int n_slots) {
-    return size_t(kEvalWarps) * (size_t(n_slots) * 32 * sizeof(float2) + kStreamStride);
+// Dynamic shared memory of an interval / float tape-walking CTA: per warp one chunk stream plus
+// 256-byte value rows - one per slot id, or kRemapRows when the stream renames slots.
+bool use_remap(int n_slots);
+static size_t walk_smem(int n_rows, bool remap) {
+    return size_t(kEvalWarps) * (size_t(n_rows) * 256 + (remap ? kStreamStrideRemap : kStreamStridePlain));
+}
+// Shared-memory value rows per warp: one per slot id, or a fixed budget when slots are renamed.
+int walk_rows(int n_slots) {
+    if (!use_remap(n_slots)) return n_slots;
+    static const char* env = getenv("MPRB_REMAP_ROWS");
+    const int rows = env ? atoi(env) : kRemapRowsDefault;
+    return rows < kRemapRowsMin ? kRemapRowsMin : (rows > 128 ? 128 : rows);
+}
+// Renaming pays once per-id rows would leave fewer than ~24 warps per SM.
+bool use_remap(int n_slots) {
+    static const char* force = getenv("MPRB_REMAP");
+    if (force) return force[0] == '1';
+    return n_slots > 36;
+}
+// Normal pass (float4 values, no stream): shared rows, or local memory for many slots.
+static size_t normals_smem(int n_slots, bool local) {
+    return local ? 0 : size_t(kEvalWarps) * n_slots * 512;
+}
+bool use_local_normals(int n_slots) {
+    static const char* force = getenv("MPRB_LOCAL_SLOTS");
+    if (force) return force[0] == '1';
+    return n_slots > 18;
 }
 
-// Also pin the L1/shared split to "all shared": occupancy here is bounded by shared memory,
-// and a device-wide cudaDeviceSetCacheConfig(PreferL1) made by other code in the process
-// (the reference's Context constructor does that, context.cpp:47-48) would otherwise shrink
-// the carve-out to one CTA per SM.
+// Also pin the L1/shared split to "all shared" for the shared-memory variants: occupancy there
+// is bounded by shared memory, and a device-wide cudaDeviceSetCacheConfig(PreferL1) made by
+// other code in the process (the reference's Context constructor does that, context.cpp:47-48)
+// would otherwise shrink the carve-out to one CTA per SM.  Local-slot variants prefer L1.
 template <typename K>
-static void opt_in(K kernel, int max_smem_optin) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+static void opt_in(K kernel, int max_smem_optin, bool local = false) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, local ? 8 * 1024 : max_smem_optin);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         local ? cudaSharedmemCarveoutMaxL1 : cudaSharedmemCarveoutMaxShared);
 }
 void init_kernels(int max_smem_optin) {
-    opt_in(k_eval_tiles<2, true>, max_smem_optin);
-    opt_in(k_eval_tiles<2, false>, max_smem_optin);
-    opt_in(k_eval_tiles<3, true>, max_smem_optin);
-    opt_in(k_eval_tiles<3, false>, max_smem_optin);
+    opt_in(k_eval_tiles<2, true, false>, max_smem_optin);
+    opt_in(k_eval_tiles<2, false, false>, max_smem_optin);
+    opt_in(k_eval_tiles<3, true, false>, max_smem_optin);
+    opt_in(k_eval_tiles<3, false, false>, max_smem_optin);
+    opt_in(k_eval_tiles<2, true, true>, max_smem_optin);
+    opt_in(k_eval_tiles<2, false, true>, max_smem_optin);
+    opt_in(k_eval_tiles<3, true, true>, max_smem_optin);
+    opt_in(k_eval_tiles<3, false, true>, max_smem_optin);
     opt_in(k_eval_root<2>, max_smem_optin);
     opt_in(k_eval_root<3>, max_smem_optin);
-    opt_in(k_eval_pixels, max_smem_optin);
-    opt_in(k_eval_voxels, max_smem_optin);
-    opt_in(k_normals, max_smem_optin);
+    opt_in(k_eval_pixels<false>, max_smem_optin);
+    opt_in(k_eval_voxels<false>, max_smem_optin);
+    opt_in(k_normals<false>, max_smem_optin);
+    opt_in(k_eval_pixels<true>, max_smem_optin);
+    opt_in(k_eval_voxels<true>, max_smem_optin);
+    opt_in(k_normals<true>, max_smem_optin, true);
 }
 
 template <int DIM, bool ROOT>
 static void launch_eval_tiles_t(const EvalTilesArgs& a, const void* mat, int grid, cudaStream_t s) {
-    const size_t smem = float_smem(a.n_slots);
-    auto kernel = k_eval_tiles<DIM, ROOT>;
-    kernel<<<grid, kEvalThreads, smem, s>>>(a, *static_cast<const typename MatOf<DIM>::type*>(mat));
+    const bool local = use_remap(a.n_slots);
+    const size_t smem = walk_smem(a.n_rows, local);
+    const auto& m = *static_cast<const typename MatOf<DIM>::type*>(mat);
+    if (local) k_eval_tiles<DIM, ROOT, true><<<grid, kEvalThreads, smem, s>>>(a, m);
+    else k_eval_tiles<DIM, ROOT, false><<<grid, kEvalThreads, smem, s>>>(a, m);
 }
 
 void launch_eval_tiles(int dim, bool root, const EvalTilesArgs& a, const void* mat, int grid, cudaStream_t s) {
@@ -1237,50 +1334,59 @@ void launch_upsample_filled(int dim, const int32_t* prev, int32_t* image, int si
 }
 
 void launch_eval_pixels(const EvalVoxelsArgs& a, const Mat3& mat, int grid, cudaStream_t s) {
-    const size_t smem = float_smem(a.n_slots);
-    k_eval_pixels<<<grid, kEvalThreads, smem, s>>>(a, mat);
+    const bool local = use_remap(a.n_slots);
+    const size_t smem = walk_smem(a.n_rows, local);
+    if (local) k_eval_pixels<true><<<grid, kEvalThreads, smem, s>>>(a, mat);
+    else k_eval_pixels<false><<<grid, kEvalThreads, smem, s>>>(a, mat);
 }
 
 void launch_eval_voxels(const EvalVoxelsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
-    const size_t smem = float_smem(a.n_slots);
-    k_eval_voxels<<<grid, kEvalThreads, smem, s>>>(a, mat);
+    const bool local = use_remap(a.n_slots);
+    const size_t smem = walk_smem(a.n_rows, local);
+    if (local) k_eval_voxels<true><<<grid, kEvalThreads, smem, s>>>(a, mat);
+    else k_eval_voxels<false><<<grid, kEvalThreads, smem, s>>>(a, mat);
 }
 
 void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
-    const size_t smem = size_t(kEvalWarps) * a.n_slots * 32 * sizeof(float4);
-    k_normals<<<grid, kEvalThreads, smem, s>>>(a, mat);
+    const bool local = use_local_normals(a.n_slots);
+    const size_t smem = normals_smem(a.n_slots, local);
+    if (local) k_normals<true><<<grid, kEvalThreads, smem, s>>>(a, mat);
+    else k_normals<false><<<grid, kEvalThreads, smem, s>>>(a, mat);
 }
 
 void launch_begin_frame(FrameCtl* ctl, int32_t first_free, cudaStream_t s) {
     k_begin_frame<<<1, 64, 0, s>>>(ctl, first_free);
 }
 
-int occupancy_eval_tiles(int dim, bool root, int n_slots) {
-    const size_t smem = float_smem(n_slots);
+template <typename K>
+static int occ(K kernel, size_t smem) {
     int n = 0;
-    if (dim == 3) {
-        if (root) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_tiles<3, true>, kEvalThreads, smem); }
-        else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_tiles<3, false>, kEvalThreads, smem); }
-    } else {
-        if (root) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_tiles<2, true>, kEvalThreads, smem); }
-        else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_tiles<2, false>, kEvalThreads, smem); }
-    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kEvalThreads, smem);
     return n;
+}
+
+int occupancy_eval_tiles(int dim, bool root, int n_slots) {
+    const bool local = use_remap(n_slots);
+    const size_t smem = walk_smem(walk_rows(n_slots), local);
+    if (dim == 3) {
+        if (root) return local ? occ(k_eval_tiles<3, true, true>, smem) : occ(k_eval_tiles<3, true, false>, smem);
+        return local ? occ(k_eval_tiles<3, false, true>, smem) : occ(k_eval_tiles<3, false, false>, smem);
+    }
+    if (root) return local ? occ(k_eval_tiles<2, true, true>, smem) : occ(k_eval_tiles<2, true, false>, smem);
+    return local ? occ(k_eval_tiles<2, false, true>, smem) : occ(k_eval_tiles<2, false, false>, smem);
 }
 
 int occupancy_eval_voxels(int dim, int n_slots) {
-    const size_t smem = float_smem(n_slots);
-    int n = 0;
-    if (dim == 3) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_voxels, kEvalThreads, smem); }
-    else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_eval_pixels, kEvalThreads, smem); }
-    return n;
+    const bool local = use_remap(n_slots);
+    const size_t smem = walk_smem(walk_rows(n_slots), local);
+    if (dim == 3) return local ? occ(k_eval_voxels<true>, smem) : occ(k_eval_voxels<false>, smem);
+    return local ? occ(k_eval_pixels<true>, smem) : occ(k_eval_pixels<false>, smem);
 }
 
 int occupancy_normals(int n_slots) {
-    const size_t smem = size_t(kEvalWarps) * n_slots * 32 * sizeof(float4);
-    int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_normals, kEvalThreads, smem);
-    return n;
+    const bool local = use_local_normals(n_slots);
+    const size_t smem = normals_smem(n_slots, local);
+    return local ? occ(k_normals<true>, smem) : occ(k_normals<false>, smem);
 }
 
 }  // namespace mprb

@@ -29,6 +29,7 @@ struct EvalTilesArgs {
     int32_t* queue;           // work-queue head for this launch
     int32_t level;            // 0, 1, 2 (statistics slot / overflow bit)
     int32_t n_slots;          // slot ids used by the root tape, +1
+    int32_t n_rows;           // shared-memory value rows per warp (walk_rows(n_slots))
     float z;                  // 2D only: the constant z
 };
 
@@ -90,6 +91,7 @@ struct EvalVoxelsArgs {
     FrameCtl* ctl;
     int32_t* queue;
     int32_t n_slots;
+    int32_t n_rows;           // shared-memory value rows per warp (walk_rows(n_slots))
     float z;
 };
 
@@ -119,6 +121,7 @@ void launch_eval_voxels(const EvalVoxelsArgs& a, const Mat4& mat, int grid, cuda
 void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_t s);
 
 // Resident CTAs per SM for a given slot count (sizes the persistent grids).
+int walk_rows(int n_slots);
 int occupancy_eval_tiles(int dim, bool root, int n_slots);
 int occupancy_eval_voxels(int dim, int n_slots);
 int occupancy_normals(int n_slots);

@@ -38,6 +38,10 @@ CASES = [
     ("involute_gear_2d", 2, 4096),
     ("bear", 3, 1024),
     ("architecture", 3, 1024),
+    ("hello_world", 2, 1024),
+    ("architecture", 3, 2048),
+    ("involute_gear_3d", 3, 2048),
+    ("bear", 3, 2048),
 ]
 
 SUBTAPES = 6400000   # the reference arm is built with -DBIG_SERVER
