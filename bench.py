@@ -150,6 +150,7 @@ def run_mine(args, workloads):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("MPRB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     class DevArray:   # wraps a raw device pointer for torch.as_tensor
@@ -158,23 +159,20 @@ def run_mine(args, workloads):
 
     jobs = []
     for model, dim, size in workloads:
-        b, e = sharding.band_rows(size, world, rank)
-        ctx = capi.Context(size, device=local, num_subtapes=SUBTAPES, row_begin=b, row_end=e)
+        ctx = capi.Context(size, device=local, num_subtapes=SUBTAPES, **sharding.cyclic_rows(size, world, rank))
         cells_pinned = torch.from_numpy(load_tape(model).view(np.int64).copy()).pin_memory()
         cells = cells_pinned.numpy().view(np.uint64)
         tape = capi.Tape(cells)
         out_img = torch.empty((size, size), dtype=torch.int32).pin_memory()
         out_nrm = torch.empty((size, size), dtype=torch.int32).pin_memory() if dim == 3 else None
         job = dict(model=model, dim=dim, size=size, ctx=ctx, tape=tape, cells=cells, keep=cells_pinned,
-                   out_img=out_img, out_nrm=out_nrm, sl=sharding.band_slice(size, world, rank))
+                   out_img=out_img, out_nrm=out_nrm)
         if world > 1:
             ptr, nbytes = ctx.device_image()
             job["dev_img"] = torch.as_tensor(DevArray(ptr, size * size, "<i4"), device=f"cuda:{local}").view(size, size)
-            job["gather"] = torch.empty((size, size), dtype=torch.int32, device=f"cuda:{local}")
             if dim == 3:
                 ptr, nbytes = ctx.device_normals()
                 job["dev_nrm"] = torch.as_tensor(DevArray(ptr, size * size, "<i4"), device=f"cuda:{local}").view(size, size)
-                job["gather_n"] = torch.empty((size, size), dtype=torch.int32, device=f"cuda:{local}")
         jobs.append(job)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
@@ -185,11 +183,10 @@ def run_mine(args, workloads):
             return 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        dist.all_gather_into_tensor(job["gather"].view(-1), job["dev_img"][job["sl"]].reshape(-1))
-        job["dev_img"].copy_(job["gather"])       # every rank ends up holding the full frame
+        # interleaved tile rows -> one all-gather per image; every rank ends up holding the full frame
+        job["dev_img"].copy_(sharding.all_gather_cyclic(job["dev_img"], job["size"]))
         if job["dim"] == 3:
-            dist.all_gather_into_tensor(job["gather_n"].view(-1), job["dev_nrm"][job["sl"]].reshape(-1))
-            job["dev_nrm"].copy_(job["gather_n"])
+            job["dev_nrm"].copy_(sharding.all_gather_cyclic(job["dev_nrm"], job["size"]))
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
@@ -300,7 +297,7 @@ def run_mine(args, workloads):
             "vs_baseline": None, "dtype": "f32", "data": "the reference's benchmark models as packed tapes (tests/golden/tapes)",
             "config": {"workload": "+".join(f"{j['model']}_{j['dim']}d_{j['size']}" for j in jobs),
                        "frames_per_step": n_frames, "view": "2D identity, 3D T(3,2)=0.3 (reference table drivers)",
-                       "parallelism": f"tile-row bands x{world}" + (", 1 NCCL all-gather/frame" if world > 1 else ""),
+                       "parallelism": f"interleaved 64-px tile rows x{world}" + (", 1 NCCL all-gather per image" if world > 1 else ""),
                        "num_subtapes": SUBTAPES, "l2": "flushed between steps (256 MiB memset, untimed)",
                        "timing": "CUDA events on the render stream per frame (+ all-gather events), max over ranks",
                        "ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(dev[:, i].mean()) for i, j in enumerate(jobs)},

@@ -63,6 +63,10 @@ typedef struct mprb_ctx_opts {
      * [row_begin, row_end) (64-pixel rows in y); row_end = 0 means "all". */
     int32_t row_begin;
     int32_t row_end;
+    /* Cyclic variant: of those rows, only rows y with y % row_mod == row_rem (row_mod <= 1: all).
+     * Interleaving tile rows across GPUs balances load far better than contiguous bands. */
+    int32_t row_mod;
+    int32_t row_rem;
 } mprb_ctx_opts;
 
 /* Per-frame counters, filled by the render calls (device-side; no extra syncs). */

@@ -90,7 +90,7 @@ struct mprb_ctx {
     int device = 0;
     int size = 0;
     int sm_count = 0;
-    int row_begin = 0, row_end = 0;
+    int row_begin = 0, row_end = 0, row_mod = 1, row_rem = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     cudaEvent_t ev_k[kMaxLaunches + 1] = {};
@@ -353,6 +353,8 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         ea.count0 = int32_t(count0);
         ea.row_begin = c->row_begin;
         ea.row_end = c->row_end;
+        ea.row_mod = c->row_mod;
+        ea.row_rem = c->row_rem;
         ea.ctl = c->ctl;
         ea.queue = &c->ctl->queue[q++];
         ea.level = l;
@@ -370,6 +372,8 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
             ra.count0 = int32_t(count0);
             ra.row_begin = c->row_begin;
             ra.row_end = c->row_end;
+            ra.row_mod = c->row_mod;
+            ra.row_rem = c->row_rem;
             ra.ctl = c->ctl;
             ra.cells = plan->cells;
             ra.sched = plan->sched;
@@ -444,6 +448,8 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         na.size = S;
         na.y_begin = c->row_begin * 64;
         na.y_end = c->row_end * 64;
+        na.row_mod = c->row_mod;
+        na.row_rem = c->row_rem;
         na.tiles0 = c->tiles[0];
         na.tiles1 = c->tiles[1];
         na.tiles2 = c->tiles[2];
@@ -543,6 +549,12 @@ int mprb_ctx_create(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx**
     c->serial_root = getenv("MPRB_SERIAL_ROOT") != nullptr;
     c->row_begin = opts ? opts->row_begin : 0;
     c->row_end = (opts && opts->row_end > 0) ? opts->row_end : tps0;
+    c->row_mod = (opts && opts->row_mod > 1) ? opts->row_mod : 1;
+    c->row_rem = (opts && opts->row_mod > 1) ? opts->row_rem : 0;
+    if (c->row_rem < 0 || c->row_rem >= c->row_mod) {
+        delete c;
+        return fail(MPRB_E_ARG, "row_rem must lie in [0, row_mod)");
+    }
     if (c->row_begin < 0 || c->row_end > tps0 || c->row_begin >= c->row_end) {
         delete c;
         return fail(MPRB_E_ARG, "tile-row band [%d, %d) is outside [0, %d)", opts ? opts->row_begin : 0,

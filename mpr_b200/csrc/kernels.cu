@@ -204,7 +204,7 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
             sx = tt % tps;
             sy = (tt / tps) % tps;
             if (DIM == 3) sz = (tt / tps) / tps;
-            inband = (sy >= a.row_begin) && (sy < a.row_end);
+            inband = (sy >= a.row_begin) && (sy < a.row_end) && (sy % a.row_mod == a.row_rem);
         } else {
             const int rank = item >> 1;
             const int sub = ((item & 1) << 5) | lane;
@@ -583,7 +583,7 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
     // Occlusion pre-mask.  The image changes under us (other tiles' atomicMax), so one
     // thread looks and the whole group follows its answer.
     if (t == 0) {
-        bool al = (sy >= a.row_begin) && (sy < a.row_end);
+        bool al = (sy >= a.row_begin) && (sy < a.row_end) && (sy % a.row_mod == a.row_rem);
         if (DIM == 3 && al && __ldcg(&a.image[img_index]) > sz) al = false;
         scratch[12] = al;
         if (!al) {
@@ -1097,6 +1097,7 @@ k_normals(const NormalsArgs a, const Mat4 mat)
         const int px = (item % blocks_x) * 8 + (lane & 7);
         const int py = a.y_begin + (item / blocks_x) * 4 + (lane >> 3);
         const int pxy = px + py * size;
+        if ((py >> 6) % a.row_mod != a.row_rem) continue;      // another context's tile row
         int pz = a.image[pxy];
         int tape = -1;
         if (pz != 0) {

@@ -24,7 +24,9 @@ struct EvalTilesArgs {
     uint32_t ptps;            // parent tiles per side
     int32_t count0;           // root level: number of tiles
     int32_t row_begin;        // root level: this context renders tile rows
-    int32_t row_end;          //   [row_begin, row_end) in y (multi-GPU sharding)
+    int32_t row_end;          //   [row_begin, row_end) in y (multi-GPU sharding) ...
+    int32_t row_mod;          //   ... of which only rows with y % row_mod == row_rem
+    int32_t row_rem;
     FrameCtl* ctl;
     int32_t* queue;           // work-queue head for this launch
     int32_t level;            // 0, 1, 2 (statistics slot / overflow bit)
@@ -53,6 +55,8 @@ struct EvalRootArgs {
     int32_t count0;
     int32_t row_begin;
     int32_t row_end;
+    int32_t row_mod;
+    int32_t row_rem;
     FrameCtl* ctl;
     const uint64_t* cells;    // the Tape's contiguous cells (header, clauses, end cell)
     const RootClause* sched;  // clauses sorted by (dependency level, opcode)
@@ -100,8 +104,10 @@ struct NormalsArgs {
     const int32_t* image;     // heightmap
     uint32_t* normals;
     int32_t size;
-    int32_t y_begin;          // pixel rows [y_begin, y_end) belong to this context
+    int32_t y_begin;          // pixel rows [y_begin, y_end) belong to this context ...
     int32_t y_end;
+    int32_t row_mod;          // ... restricted to 64-px tile rows with row % row_mod == row_rem
+    int32_t row_rem;
     const TileNode* tiles0;
     const TileNode* tiles1;
     const TileNode* tiles2;

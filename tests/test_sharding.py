@@ -32,6 +32,10 @@ def _worker(rank, world, port, size, full_path, out_path):
     local[sl] = full[sl]                        # this rank only "rendered" its band
     got = sharding.all_gather_bands(local, size)
     ok = bool(torch.equal(got, full))
+    owner = (torch.arange(size) // 64) % world
+    local2 = torch.zeros_like(full)
+    local2[owner == rank] = full[owner == rank]            # interleaved assignment
+    ok = ok and bool(torch.equal(sharding.all_gather_cyclic(local2, size), full))
     np.save(out_path.format(rank), np.array([ok]))
     dist.destroy_process_group()
 
