@@ -10,7 +10,7 @@ CU_SRCS   := mpr_b200/csrc/kernels.cu mpr_b200/csrc/api.cu
 CXX_SRCS  := mpr_b200/csrc/host/tree.cpp mpr_b200/csrc/host/tape_build.cpp mpr_b200/csrc/host/cxx_api.cpp
 OBJS      := $(patsubst %.cu,$(BUILD)/%.o,$(CU_SRCS)) $(patsubst %.cpp,$(BUILD)/%.o,$(CXX_SRCS))
 
-all: mpr_b200/libmprb.so
+all: mpr_b200/libmprb.so drivers
 
 mpr_b200/libmprb.so: $(OBJS)
 	$(NVCC) -shared $(ARCH) -Xlinker -Bsymbolic -o $@ $(OBJS)

@@ -207,7 +207,8 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
             inband = (sy >= a.row_begin) && (sy < a.row_end) && (sy % a.row_mod == a.row_rem);
         } else {
             const int rank = item >> 1;
-            const int sub = ((item & 1) << 5) | lane;
+            // 3D: the upper half of the children (z = 2, 3) goes first, for the same reason
+            const int sub = DIM == 3 ? ((((item & 1) ^ 1) << 5) | lane) : (((item & 1) << 5) | lane);
             const TileNode parent = a.ptiles[a.pactive[rank]];
             tape = parent.tape;
             tile_index = rank * 64 + sub;
@@ -821,7 +822,11 @@ k_rank_tiles(const RankArgs a)
     const int lane = lane_id();
     const int stride = gridDim.x * blockDim.x;
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n_tiles; base += stride) {
-        const int t = base + lane;
+        // 3D: visit each parent's 64 children highest-z first (sub = x + 4y + 16z), so that ranks -
+        // and with them the order in which the next pass takes tiles - run front to back and the
+        // occlusion early-outs see the surface before what lies behind it.
+        int t = base + lane;
+        if (DIM == 3 && a.n_parents) t = (t & ~63) | (63 - (t & 63));
         bool active = false;
         TileNode node = {-1, 0, -1};
         if (t < n_tiles) {
@@ -953,7 +958,7 @@ __device__ __forceinline__ float2 walk_float(TapeStream<REMAP>& ts, int tape, Sl
 
 // 2D: one warp per surviving 8x8 tile, two pixels per lane (y and y + 4).
 template <bool REMAP>
-__global__ void __launch_bounds__(kEvalThreads)
+__global__ void __launch_bounds__(kFloatThreads)
 k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -964,7 +969,7 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
     ts.init(s_dyn + warp * Stream::stride(), a.arena);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
     Slots2<REMAP> slots;
-    slots.base = smem_addr(s_dyn + kEvalWarps * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
+    slots.base = smem_addr(s_dyn + kFloatWarps * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
     slots.limit = uint32_t(n_rows) * 256u;
     const uint64_t* const arena = a.arena;
     unsigned long long st_tiles = 0, st_cells = 0;
@@ -1010,7 +1015,7 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 // list is roughly front-to-back and the per-lane early-out below (the
 // reference's, context.cu:852-864) culls most of what lies behind the surface.
 template <bool REMAP>
-__global__ void __launch_bounds__(kEvalThreads)
+__global__ void __launch_bounds__(kFloatThreads)
 k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -1021,7 +1026,7 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
     ts.init(s_dyn + warp * Stream::stride(), a.arena);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
     Slots2<REMAP> slots;
-    slots.base = smem_addr(s_dyn + kEvalWarps * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
+    slots.base = smem_addr(s_dyn + kFloatWarps * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
     slots.limit = uint32_t(n_rows) * 256u;
     const uint64_t* const arena = a.arena;
     unsigned long long st_tiles = 0, st_cells = 0;
@@ -1242,8 +1247,8 @@ __global__ void k_begin_frame(FrameCtl* ctl, int32_t first_free)
 // Dynamic shared memory of an interval / float tape-walking CTA: per warp one chunk stream plus
 // 256-byte value rows - one per slot id, or kRemapRows when the stream renames slots.
 bool use_remap(int n_slots);
-static size_t walk_smem(int n_rows, bool remap) {
-    return size_t(kEvalWarps) * (size_t(n_rows) * 256 + (remap ? kStreamStrideRemap : kStreamStridePlain));
+static size_t walk_smem(int n_rows, bool remap, int warps = kEvalWarps) {
+    return size_t(warps) * (size_t(n_rows) * 256 + (remap ? kStreamStrideRemap : kStreamStridePlain));
 }
 // Shared-memory value rows per warp: one per slot id, or a fixed budget when slots are renamed.
 int walk_rows(int n_slots) {
@@ -1336,16 +1341,16 @@ void launch_upsample_filled(int dim, const int32_t* prev, int32_t* image, int si
 
 void launch_eval_pixels(const EvalVoxelsArgs& a, const Mat3& mat, int grid, cudaStream_t s) {
     const bool local = use_remap(a.n_slots);
-    const size_t smem = walk_smem(a.n_rows, local);
-    if (local) k_eval_pixels<true><<<grid, kEvalThreads, smem, s>>>(a, mat);
-    else k_eval_pixels<false><<<grid, kEvalThreads, smem, s>>>(a, mat);
+    const size_t smem = walk_smem(a.n_rows, local, kFloatWarps);
+    if (local) k_eval_pixels<true><<<grid, kFloatThreads, smem, s>>>(a, mat);
+    else k_eval_pixels<false><<<grid, kFloatThreads, smem, s>>>(a, mat);
 }
 
 void launch_eval_voxels(const EvalVoxelsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
     const bool local = use_remap(a.n_slots);
-    const size_t smem = walk_smem(a.n_rows, local);
-    if (local) k_eval_voxels<true><<<grid, kEvalThreads, smem, s>>>(a, mat);
-    else k_eval_voxels<false><<<grid, kEvalThreads, smem, s>>>(a, mat);
+    const size_t smem = walk_smem(a.n_rows, local, kFloatWarps);
+    if (local) k_eval_voxels<true><<<grid, kFloatThreads, smem, s>>>(a, mat);
+    else k_eval_voxels<false><<<grid, kFloatThreads, smem, s>>>(a, mat);
 }
 
 void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
@@ -1360,9 +1365,9 @@ void launch_begin_frame(FrameCtl* ctl, int32_t first_free, cudaStream_t s) {
 }
 
 template <typename K>
-static int occ(K kernel, size_t smem) {
+static int occ(K kernel, size_t smem, int threads = kEvalThreads) {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kEvalThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem);
     return n;
 }
 
@@ -1379,9 +1384,9 @@ int occupancy_eval_tiles(int dim, bool root, int n_slots) {
 
 int occupancy_eval_voxels(int dim, int n_slots) {
     const bool local = use_remap(n_slots);
-    const size_t smem = walk_smem(walk_rows(n_slots), local);
-    if (dim == 3) return local ? occ(k_eval_voxels<true>, smem) : occ(k_eval_voxels<false>, smem);
-    return local ? occ(k_eval_pixels<true>, smem) : occ(k_eval_pixels<false>, smem);
+    const size_t smem = walk_smem(walk_rows(n_slots), local, kFloatWarps);
+    if (dim == 3) return local ? occ(k_eval_voxels<true>, smem, kFloatThreads) : occ(k_eval_voxels<false>, smem, kFloatThreads);
+    return local ? occ(k_eval_pixels<true>, smem, kFloatThreads) : occ(k_eval_pixels<false>, smem, kFloatThreads);
 }
 
 int occupancy_normals(int n_slots) {

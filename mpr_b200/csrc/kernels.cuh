@@ -7,7 +7,12 @@
 
 namespace mprb {
 
-constexpr int kEvalWarps = 4;                 // warps per CTA in the tape-walking kernels
+constexpr int kEvalWarps = 4;                 // warps per CTA: interval and normal passes
+// The float pass runs ONE warp per CTA: everything warp-uniform (clause words, tape pointers) is
+// then CTA-uniform, which lets ptxas drop most of the divergence bookkeeping in the clause loop
+// (-5 % on bear); the other passes lose more from the 32-CTA/SM limit than they gain.
+constexpr int kFloatWarps = 1;
+constexpr int kFloatThreads = kFloatWarps * 32;
 constexpr int kEvalThreads = kEvalWarps * 32;
 
 struct EvalTilesArgs {
