@@ -117,6 +117,31 @@ int mprb_render3d_host(mprb_ctx* ctx, const uint64_t* host_cells, int32_t n_cell
 
 int mprb_frame_stats_get(mprb_ctx* ctx, mprb_frame_stats* out);
 
+/* ---- analysis variants ---------------------------------------------------------------- */
+/* Context::render2D_brute (src/context.cu:1461-1508): no subdivision; every 8x8 tile of the
+ * frame is evaluated point by point with the full tape. */
+int mprb_render2d_brute(mprb_ctx* ctx, const mprb_tape* tape, const float mat3_colmajor[9], float z);
+/* Context::render2D_heatmap / render3D_heatmap (src/context.cu:1984-2340): a normal frame that
+ * also accumulates the amortised work per pixel (tape cells walked by every tile covering the
+ * pixel, divided by the tile's pixel count), normalised by the clause count of the tape.
+ * *heatmap_out: size*size floats of managed memory owned by the caller (mprb_free_device). */
+int mprb_render2d_heatmap(mprb_ctx* ctx, const mprb_tape* tape, const float mat3_colmajor[9], float z,
+                          float** heatmap_out);
+int mprb_render3d_heatmap(mprb_ctx* ctx, const mprb_tape* tape, const float mat4_colmajor[16],
+                          float** heatmap_out);
+
+/* ---- post-effects: mpr::Effects (inc/effects.hpp:21-37, src/effects.cu:229-297) ---- */
+typedef struct mprb_effects mprb_effects;
+/* ssao_kernel: 64x3, ssao_rvecs: 256x3, both column-major floats (the Eigen members the
+ * reference's Effects constructor fills with rand()). */
+int mprb_effects_create(const float* ssao_kernel_64x3, const float* ssao_rvecs_256x3, mprb_effects** out);
+void mprb_effects_destroy(mprb_effects* fx);
+/* Effects::drawSSAO / drawShaded on the context's last 3D frame; the result is `image`. */
+int mprb_effects_draw_ssao(mprb_effects* fx, mprb_ctx* ctx);
+int mprb_effects_draw_shaded(mprb_effects* fx, mprb_ctx* ctx);
+/* Effects::image / Effects::tmp (managed memory, size*size int32 each). */
+int mprb_effects_buffers(mprb_effects* fx, int32_t** image, int32_t** tmp);
+
 /* ---- host helpers ----------------------------------------------------------------- */
 /* .frep bytes -> packed tape (libfive archive reader + the packer that restates
  * src/tape.cpp).  *cells_out is malloc'd; release with mprb_free(). */
@@ -125,6 +150,8 @@ int mprb_tape_from_frep(const uint8_t* bytes, size_t n_bytes, int simplify,
 void mprb_free(void* p);
 /* Releases device / managed memory (cudaFree); counterpart of CUDA_FREE in inc/util.hpp. */
 void mprb_free_device(void* p);
+/* Managed allocation; counterpart of CUDA_MALLOC (cudaMallocManaged) in inc/util.hpp:26-33. */
+int mprb_malloc_managed(size_t n_bytes, void** out);
 
 const char* mprb_last_error(void);
 const char* mprb_version(void);

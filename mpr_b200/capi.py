@@ -79,7 +79,9 @@ EXPORTS = [
     "mprb_tape_create", "mprb_tape_destroy", "mprb_tape_data", "mprb_tape_length",
     "mprb_tape_num_slots", "mprb_render2d", "mprb_render3d", "mprb_render2d_host",
     "mprb_render3d_host", "mprb_frame_stats_get", "mprb_tape_from_frep", "mprb_free", "mprb_free_device",
-    "mprb_last_error", "mprb_version",
+    "mprb_last_error", "mprb_version", "mprb_effects_create", "mprb_effects_destroy",
+    "mprb_effects_draw_ssao", "mprb_effects_draw_shaded", "mprb_effects_buffers",
+    "mprb_malloc_managed", "mprb_render2d_brute", "mprb_render2d_heatmap", "mprb_render3d_heatmap",
 ]
 
 _lib = None
@@ -119,6 +121,15 @@ def lib():
                                       C.POINTER(i32), C.POINTER(i32)]
     L.mprb_free.argtypes = [C.c_void_p]
     L.mprb_free.restype = None
+    L.mprb_render2d_brute.argtypes = [vp, vp, C.c_void_p, C.c_float]
+    L.mprb_render2d_heatmap.argtypes = [vp, vp, C.c_void_p, C.c_float, C.POINTER(C.POINTER(C.c_float))]
+    L.mprb_render3d_heatmap.argtypes = [vp, vp, C.c_void_p, C.POINTER(C.POINTER(C.c_float))]
+    L.mprb_effects_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(vp)]
+    L.mprb_effects_destroy.argtypes = [vp]
+    L.mprb_effects_destroy.restype = None
+    L.mprb_effects_draw_ssao.argtypes = [vp, vp]
+    L.mprb_effects_draw_shaded.argtypes = [vp, vp]
+    L.mprb_effects_buffers.argtypes = [vp, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32))]
     L.mprb_last_error.restype = C.c_char_p
     L.mprb_version.restype = C.c_char_p
     _lib = L
@@ -181,6 +192,66 @@ class Tape:
             pass
 
 
+def glibc_effect_samples():
+    """The SSAO sample sets exactly as mpr::Effects::Effects() draws them (src/effects.cu:229-250):
+    glibc rand() from its default seed, 64x3 kernel then 256x3 rotation vectors, column-major."""
+    libc = C.CDLL("libc.so.6")
+    libc.srand(1)
+    rmax = 2147483647.0
+    def r():
+        return np.float32(np.float32(libc.rand()) / np.float32(rmax))
+    kernel = np.zeros((64, 3), dtype=np.float32)
+    for i in range(64):
+        v = np.array([np.float32(2.0) * (r() - np.float32(0.5)), np.float32(2.0) * (r() - np.float32(0.5)), r()],
+                     dtype=np.float32)
+        v = v / np.float32(np.sqrt(np.float32((v * v).sum(dtype=np.float32))))
+        scale = np.float32(i) / np.float32(63)
+        scale = (scale * scale) * np.float32(0.9) + np.float32(0.1)
+        kernel[i] = v * scale
+    rvecs = np.zeros((256, 3), dtype=np.float32)
+    for i in range(256):
+        v = np.array([np.float32(2.0) * (r() - np.float32(0.5)), np.float32(2.0) * (r() - np.float32(0.5)), 0.0],
+                     dtype=np.float32)
+        rvecs[i] = v / np.float32(np.sqrt(np.float32((v * v).sum(dtype=np.float32))))
+    return np.asfortranarray(kernel), np.asfortranarray(rvecs)
+
+
+class Effects:
+    """Mirror of mpr::Effects (reference inc/effects.hpp:21-37)."""
+
+    def __init__(self, kernel=None, rvecs=None):
+        if kernel is None:
+            kernel, rvecs = glibc_effect_samples()
+        self.kernel = np.asfortranarray(kernel, dtype=np.float32)
+        self.rvecs = np.asfortranarray(rvecs, dtype=np.float32)
+        self._h = C.c_void_p()
+        _check(lib().mprb_effects_create(self.kernel.ctypes.data, self.rvecs.ctypes.data, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().mprb_effects_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def drawSSAO(self, ctx):
+        _check(lib().mprb_effects_draw_ssao(self._h, ctx._h))
+        self._size = ctx.image_size_px
+
+    def drawShaded(self, ctx):
+        _check(lib().mprb_effects_draw_shaded(self._h, ctx._h))
+        self._size = ctx.image_size_px
+
+    def image(self):
+        img = C.POINTER(C.c_int32)()
+        _check(lib().mprb_effects_buffers(self._h, C.byref(img), None))
+        return np.ctypeslib.as_array(img, shape=(self._size, self._size))
+
+
 class Context:
     """Mirror of mpr::Context (reference inc/context.hpp:38-73)."""
 
@@ -212,6 +283,28 @@ class Context:
     def render3D(self, tape: Tape, mat=None):
         m = mat_colmajor(view_matrix_3d() if mat is None else mat)
         _check(lib().mprb_render3d(self._h, tape._h, m.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def render2D_brute(self, tape: Tape, mat=None, z: float = 0.0):
+        m = mat_colmajor(np.eye(3) if mat is None else mat)
+        _check(lib().mprb_render2d_brute(self._h, tape._h, m.ctypes.data, z))
+
+    def _take_heatmap(self, ptr):
+        s = self.image_size_px
+        out = np.ctypeslib.as_array(ptr, shape=(s, s)).copy()
+        lib().mprb_free_device(ptr)
+        return out
+
+    def render2D_heatmap(self, tape: Tape, mat=None, z: float = 0.0):
+        m = mat_colmajor(np.eye(3) if mat is None else mat)
+        h = C.POINTER(C.c_float)()
+        _check(lib().mprb_render2d_heatmap(self._h, tape._h, m.ctypes.data, z, C.byref(h)))
+        return self._take_heatmap(h)
+
+    def render3D_heatmap(self, tape: Tape, mat=None):
+        m = mat_colmajor(view_matrix_3d() if mat is None else mat)
+        h = C.POINTER(C.c_float)()
+        _check(lib().mprb_render3d_heatmap(self._h, tape._h, m.ctypes.data, C.byref(h)))
+        return self._take_heatmap(h)
 
     def render2D_host(self, cells: np.ndarray, image_out: np.ndarray, mat=None, z: float = 0.0):
         m = mat_colmajor(np.eye(3) if mat is None else mat)

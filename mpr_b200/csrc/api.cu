@@ -24,6 +24,7 @@
 #include "../../include/mprb.h"
 #include "common.cuh"
 #include "host/mprb_host.hpp"
+#include "effects.cuh"
 #include "kernels.cuh"
 #include "libfive/tree/archive.hpp"
 
@@ -114,6 +115,7 @@ struct mprb_ctx {
     uint64_t* stage_cells = nullptr; // pinned staging for host tapes
     int32_t stage_cells_cap = 0;
     bool serial_root = false;        // debugging / A-B switch: MPRB_SERIAL_ROOT=1
+    unsigned long long* heat_units = nullptr;   // work meter of render*_heatmap (device, S*S), lazily allocated
     // Host-buffer entry points: the per-tape root plan is cached across frames as long as
     // the caller keeps passing the same cells (the cells themselves are re-uploaded every frame).
     mprb_tape* host_plan = nullptr;
@@ -269,7 +271,8 @@ struct Timer {
 
 // The frame proper.  `cells` may be a device/managed pointer (async D2D copy)
 // or a host pointer (async H2D copy through pinned staging).
-int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, const float* matrix, float z)
+int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, const float* matrix, float z,
+           bool heat = false, bool brute = false)
 {
     if (!c || !plan) return fail(MPRB_E_ARG, "null context or tape");
     const int S = c->size;
@@ -314,6 +317,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         // Host-buffer entry points pay the upload every frame: host cells -> pinned staging -> HBM.
         if (c->stage_cells_cap < n_chunked) {
             if (c->stage_cells) cudaFreeHost(c->stage_cells);
+    if (c->heat_units) cudaFree(c->heat_units);
             c->stage_cells = nullptr;
             MPRB_CUDA(cudaMallocHost(&c->stage_cells, sizeof(uint64_t) * size_t(n_chunked)));
             c->stage_cells_cap = n_chunked;
@@ -327,10 +331,26 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
     }
     MPRB_CUDA(cudaMemsetAsync(c->filled[0], 0, sizeof(int32_t) * size_t(tps0) * tps0, s));
     if (dim == 3) MPRB_CUDA(cudaMemsetAsync(c->normals, 0, sizeof(uint32_t) * size_t(S) * S, s));
+    unsigned long long* heat_units = nullptr;
+    if (heat) {
+        if (!c->heat_units) MPRB_CUDA(cudaMalloc(&c->heat_units, sizeof(unsigned long long) * size_t(S) * S));
+        heat_units = c->heat_units;
+        MPRB_CUDA(cudaMemsetAsync(heat_units, 0, sizeof(unsigned long long) * size_t(S) * S, s));
+    }
 
     int q = 0;
     const int small_grid = c->sm_count * 4;
-    for (int l = 0; l < n_levels; ++l) {
+    if (brute) {
+        // Context::render2D_brute (context.cu:1461-1508): no interval levels; every 8x8 tile goes
+        // to the float pass with the root tape.
+        const long long count = (long long)(S / 8) * (S / 8);
+        if (int e = ensure_stage(c, 3, count)) return e;
+        MPRB_CUDA(cudaMemsetAsync(c->filled[3], 0, sizeof(int32_t) * size_t(S) * S, s));
+        launch_preload_tiles(c->tiles[3], int32_t(count), &c->ctl->n_active[n_levels - 1],
+                             int(std::min<long long>(small_grid, (count + 255) / 256)), s);
+        tm.mark();
+    }
+    for (int l = 0; l < n_levels && !brute; ++l) {
         const int st = stage_of[l];
         const bool root = (l == 0);
         const bool last = (l == n_levels - 1);
@@ -361,7 +381,10 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         ea.n_slots = n_slots;
         ea.n_rows = walk_rows(n_slots);
         ea.z = z;
-        if (root && plan->group > 0 && !c->serial_root) {
+        ea.heat = heat_units;
+        ea.heat_px = px_of[l];
+        ea.n_root = n_cells - 2;
+        if (root && plan->group > 0 && !c->serial_root && !heat) {
             EvalRootArgs ra = {};
             ra.arena = c->arena;
             ra.tape_index = &c->ctl->tape_cursor;
@@ -435,6 +458,8 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         va.n_slots = n_slots;
         va.n_rows = walk_rows(n_slots);
         va.z = z;
+        va.heat = heat_units;
+        va.n_root = n_cells - 2;
         const int grid = c->sm_count * cached_occupancy(c, 1, dim, false, n_slots);
         if (dim == 2) launch_eval_pixels(va, m3, grid, s);
         else launch_eval_voxels(va, m4, grid, s);
@@ -743,6 +768,37 @@ int mprb_render3d(mprb_ctx* c, const mprb_tape* t, const float mat4[16]) {
     return finish(c, 3);
 }
 
+int mprb_render2d_brute(mprb_ctx* c, const mprb_tape* t, const float mat3[9], float z) {
+    if (!c || !t || !mat3) return fail(MPRB_E_ARG, "null argument");
+    if (int e = render(c, 2, t, false, mat3, z, false, true)) return e;
+    return finish(c, 2);
+}
+
+// Managed S*S float result, owned by the caller (the reference returns a Ptr<float[]>).
+static int heatmap_out(mprb_ctx* c, const mprb_tape* t, float** out) {
+    const size_t n = size_t(c->size) * c->size;
+    float* h = nullptr;
+    MPRB_CUDA(managed_alloc(&h, n, c->device));
+    launch_heat_finish(c->heat_units, h, (long long)n, t->length - 2,
+                       int(std::min<size_t>(size_t(c->sm_count) * 8, (n + 255) / 256)), c->stream);
+    *out = h;
+    return MPRB_OK;
+}
+
+int mprb_render2d_heatmap(mprb_ctx* c, const mprb_tape* t, const float mat3[9], float z, float** heatmap) {
+    if (!c || !t || !mat3 || !heatmap) return fail(MPRB_E_ARG, "null argument");
+    if (int e = render(c, 2, t, false, mat3, z, true)) return e;
+    if (int e = heatmap_out(c, t, heatmap)) return e;
+    return finish(c, 2);
+}
+
+int mprb_render3d_heatmap(mprb_ctx* c, const mprb_tape* t, const float mat4[16], float** heatmap) {
+    if (!c || !t || !mat4 || !heatmap) return fail(MPRB_E_ARG, "null argument");
+    if (int e = render(c, 3, t, false, mat4, 0.0f, true)) return e;
+    if (int e = heatmap_out(c, t, heatmap)) return e;
+    return finish(c, 3);
+}
+
 int mprb_render2d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
                        const float mat3[9], float z, int32_t* image_out) {
     if (!c || !mat3) return fail(MPRB_E_ARG, "null argument");
@@ -769,6 +825,84 @@ int mprb_render3d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
     if (normals_out)
         MPRB_CUDA(cudaMemcpyAsync(normals_out, c->normals, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
     return finish(c, 3);
+}
+
+struct mprb_effects {
+    float* kernel = nullptr;     // device, 64x3
+    float* rvecs = nullptr;      // device, 256x3
+    int32_t* image = nullptr;    // managed
+    int32_t* tmp = nullptr;      // managed
+    int size = 0;
+};
+
+static int effects_resize(mprb_effects* fx, mprb_ctx* c) {
+    if (fx->size == c->size) return MPRB_OK;
+    if (fx->image) cudaFree(fx->image);
+    if (fx->tmp) cudaFree(fx->tmp);
+    fx->image = fx->tmp = nullptr;
+    const size_t n = size_t(c->size) * c->size;
+    MPRB_CUDA(managed_alloc(&fx->image, n, c->device));
+    MPRB_CUDA(managed_alloc(&fx->tmp, n, c->device));
+    fx->size = c->size;
+    return MPRB_OK;
+}
+
+int mprb_effects_create(const float* kernel, const float* rvecs, mprb_effects** out) {
+    if (!kernel || !rvecs || !out) return fail(MPRB_E_ARG, "null argument");
+    mprb_effects* fx = new mprb_effects;
+    cudaError_t e = cudaMalloc(&fx->kernel, sizeof(float) * 64 * 3);
+    if (e == cudaSuccess) e = cudaMalloc(&fx->rvecs, sizeof(float) * 256 * 3);
+    if (e == cudaSuccess) e = cudaMemcpy(fx->kernel, kernel, sizeof(float) * 64 * 3, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(fx->rvecs, rvecs, sizeof(float) * 256 * 3, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        mprb_effects_destroy(fx);
+        return fail(MPRB_E_CUDA, "effects: %s", cudaGetErrorString(e));
+    }
+    *out = fx;
+    return MPRB_OK;
+}
+
+void mprb_effects_destroy(mprb_effects* fx) {
+    if (!fx) return;
+    if (fx->kernel) cudaFree(fx->kernel);
+    if (fx->rvecs) cudaFree(fx->rvecs);
+    if (fx->image) cudaFree(fx->image);
+    if (fx->tmp) cudaFree(fx->tmp);
+    delete fx;
+}
+
+int mprb_effects_draw_ssao(mprb_effects* fx, mprb_ctx* c) {
+    if (!fx || !c) return fail(MPRB_E_ARG, "null argument");
+    MPRB_CUDA(cudaSetDevice(c->device));
+    if (int e = effects_resize(fx, c)) return e;
+    const size_t bytes = sizeof(int32_t) * size_t(c->size) * c->size;
+    MPRB_CUDA(cudaMemsetAsync(fx->tmp, 0, bytes, c->stream));
+    MPRB_CUDA(cudaMemsetAsync(fx->image, 0, bytes, c->stream));
+    launch_draw_ssao(c->filled[3], c->normals, fx->kernel, fx->rvecs, c->size, fx->tmp, c->stream);
+    launch_blur_ssao(c->filled[3], fx->tmp, c->size, fx->image, c->stream);
+    MPRB_CUDA(cudaStreamSynchronize(c->stream));
+    return MPRB_OK;
+}
+
+int mprb_effects_draw_shaded(mprb_effects* fx, mprb_ctx* c) {
+    if (!fx || !c) return fail(MPRB_E_ARG, "null argument");
+    MPRB_CUDA(cudaSetDevice(c->device));
+    if (int e = effects_resize(fx, c)) return e;
+    const size_t bytes = sizeof(int32_t) * size_t(c->size) * c->size;
+    MPRB_CUDA(cudaMemsetAsync(fx->tmp, 0, bytes, c->stream));
+    MPRB_CUDA(cudaMemsetAsync(fx->image, 0, bytes, c->stream));
+    launch_draw_ssao(c->filled[3], c->normals, fx->kernel, fx->rvecs, c->size, fx->image, c->stream);
+    launch_blur_ssao(c->filled[3], fx->image, c->size, fx->tmp, c->stream);
+    launch_draw_shaded(c->filled[3], c->normals, fx->tmp, c->size, fx->image, c->stream);
+    MPRB_CUDA(cudaStreamSynchronize(c->stream));
+    return MPRB_OK;
+}
+
+int mprb_effects_buffers(mprb_effects* fx, int32_t** image, int32_t** tmp) {
+    if (!fx) return fail(MPRB_E_ARG, "null argument");
+    if (image) *image = fx->image;
+    if (tmp) *tmp = fx->tmp;
+    return MPRB_OK;
 }
 
 int mprb_frame_stats_get(mprb_ctx* c, mprb_frame_stats* out) {
@@ -799,5 +933,12 @@ int mprb_tape_from_frep(const uint8_t* bytes, size_t n_bytes, int simplify,
 
 void mprb_free(void* p) { free(p); }
 void mprb_free_device(void* p) { if (p) cudaFree(p); }
+
+int mprb_malloc_managed(size_t n_bytes, void** out) {
+    if (!out) return fail(MPRB_E_ARG, "null argument");
+    *out = nullptr;
+    MPRB_CUDA(cudaMallocManaged(out, n_bytes ? n_bytes : 1));
+    return MPRB_OK;
+}
 
 }  // extern "C"

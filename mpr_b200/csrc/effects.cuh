@@ -1,0 +1,12 @@
+// Launchers of the post-effect kernels (effects.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mprb {
+void launch_draw_ssao(const int32_t* depth, const uint32_t* norm, const float* kernel, const float* rvecs,
+                      int size, int32_t* out, cudaStream_t s);
+void launch_blur_ssao(const int32_t* image, const int32_t* ssao, int size, int32_t* out, cudaStream_t s);
+void launch_draw_shaded(const int32_t* depth, const uint32_t* norm, const int32_t* ssao, int size, int32_t* out,
+                        cudaStream_t s);
+}  // namespace mprb

@@ -3,6 +3,7 @@
 // Heightmap PNG output.
 #include <cstring>
 #include <fstream>
+#include <limits>
 #include <vector>
 
 #include "libfive/render/discrete/heightmap.hpp"
@@ -110,16 +111,25 @@ bool write_png(const std::string& name, unsigned w, unsigned h, int color_type, 
 
 namespace libfive {
 
+// Same pixel mapping as libfive (src/render/discrete/heightmap.cpp:378-399): empty (-inf) pixels
+// are black, the finite range maps to 1..65535, and the image is written bottom row first.
 bool Heightmap::savePNG(std::string filename) {
     const unsigned h = unsigned(depth.rows()), w = unsigned(depth.cols());
-    const float lo = depth.minCoeff(), hi = depth.maxCoeff();
-    const float scale = hi > lo ? 65535.0f / (hi - lo) : 0.0f;
+    const float ninf = -std::numeric_limits<float>::infinity();
+    const float zmax = depth.maxCoeff();
+    float zmin = zmax;
+    for (unsigned r = 0; r < h; ++r)
+        for (unsigned c = 0; c < w; ++c)
+            if (depth(r, c) != ninf && depth(r, c) < zmin) zmin = depth(r, c);
     std::vector<uint8_t> rows;
     rows.reserve(size_t(h) * (1 + 2 * size_t(w)));
-    for (unsigned r = 0; r < h; ++r) {
+    for (unsigned k = 0; k < h; ++k) {
+        const unsigned r = h - 1 - k;
         rows.push_back(0);
         for (unsigned c = 0; c < w; ++c) {
-            const unsigned v = unsigned((depth(r, c) - lo) * scale);
+            const float d = depth(r, c);
+            const float sc = (zmax == zmin) ? (d - zmin) + 65535.0f : (d - zmin) * 65534.0f / (zmax - zmin) + 1.0f;
+            const unsigned v = (d == ninf || !(sc > 0.0f)) ? 0u : (sc >= 65535.0f ? 65535u : unsigned(sc));
             rows.push_back(uint8_t(v >> 8));
             rows.push_back(uint8_t(v));
         }
@@ -131,7 +141,8 @@ bool Heightmap::saveNormalPNG(std::string filename) {
     const unsigned h = unsigned(norm.rows()), w = unsigned(norm.cols());
     std::vector<uint8_t> rows;
     rows.reserve(size_t(h) * (1 + 4 * size_t(w)));
-    for (unsigned r = 0; r < h; ++r) {
+    for (unsigned k = 0; k < h; ++k) {
+        const unsigned r = h - 1 - k;
         rows.push_back(0);
         for (unsigned c = 0; c < w; ++c) {
             const uint32_t p = norm(r, c);

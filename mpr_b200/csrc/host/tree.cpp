@@ -12,6 +12,8 @@
 #include <cstring>
 #include <fstream>
 #include <istream>
+#include <list>
+#include <map>
 #include <iostream>
 #include <tuple>
 
@@ -82,6 +84,7 @@ struct Tables {
     std::weak_ptr<Tree::Tree_> nan_constant;
     std::map<Key, std::weak_ptr<Tree::Tree_>> ops;
     bool simplify = true;
+    uint64_t next_serial = 1;
 };
 
 Tables& tables() {
@@ -96,6 +99,7 @@ Node constant(float v) {
         if (!n) {
             n.reset(new Tree::Tree_{Opcode::CONSTANT, Tree::FLAG_LOCATION_AGNOSTIC, 0, v,
                                     nullptr, nullptr});
+            n->serial = T.next_serial++;
             T.nan_constant = n;
         }
         return n;
@@ -105,6 +109,7 @@ Node constant(float v) {
         if (Node n = itr->second.lock()) return n;
     }
     Node n(new Tree::Tree_{Opcode::CONSTANT, Tree::FLAG_LOCATION_AGNOSTIC, 0, v, nullptr, nullptr});
+    n->serial = T.next_serial++;
     T.constants[v] = n;
     return n;
 }
@@ -207,12 +212,99 @@ Node checkCommutative(Opcode::Opcode op, const Node& a, const Node& b) {
     return nullptr;
 }
 
+// Affine collapse (libfive cache.cpp:185-301, :463-501): an ADD/SUB whose two sides share a term
+// is rewritten as sum(positive groups) - sum(negative groups), terms grouped by coefficient.
+// libfive keys its term maps on node ADDRESSES, so the order of terms inside a group depends on
+// the allocator; creation order is used here, which is what a bump-style allocator gives.
+struct BySerial {
+    bool operator()(const Node& a, const Node& b) const { return a->serial < b->serial; }
+};
+typedef std::map<Node, float, BySerial> Affine;
+
+Affine asAffine(const Node& n) {
+    using namespace Opcode;
+    Affine out;
+    if (n->op == OP_ADD) {
+        out = asAffine(n->lhs);
+        for (const auto& i : asAffine(n->rhs)) {
+            auto f = out.find(i.first);
+            if (f == out.end()) out.insert(i); else f->second += i.second;
+        }
+    } else if (n->op == OP_SUB) {
+        out = asAffine(n->lhs);
+        for (const auto& i : asAffine(n->rhs)) {
+            auto f = out.find(i.first);
+            if (f == out.end()) out.insert({i.first, -i.second}); else f->second -= i.second;
+        }
+    } else if (n->op == OP_NEG) {
+        for (const auto& i : asAffine(n->lhs)) out.insert({i.first, -i.second});
+    } else if (n->op == OP_MUL) {
+        if (n->lhs->op == CONSTANT) {
+            for (const auto& i : asAffine(n->rhs)) out.insert({i.first, i.second * n->lhs->value});
+        } else if (n->rhs->op == CONSTANT) {
+            for (const auto& i : asAffine(n->lhs)) out.insert({i.first, i.second * n->rhs->value});
+        } else {
+            out.insert({n, 1.0f});
+        }
+    } else if (n->op == OP_DIV) {
+        if (n->rhs->op == CONSTANT) {
+            for (const auto& i : asAffine(n->lhs)) out.insert({i.first, i.second / n->rhs->value});
+        } else {
+            out.insert({n, 1.0f});
+        }
+    } else if (n->op == CONSTANT) {
+        out.insert({constant(1.0f), n->value});
+    } else {
+        out.insert({n, 1.0f});
+    }
+    return out;
+}
+
+Node fromAffine(const Affine& ns) {
+    std::map<float, std::list<Node>> cs;
+    for (const auto& n : ns) cs[n.second].push_back(n.first);
+    typedef std::list<std::pair<float, std::list<Node>>> Groups;
+    Groups pos, neg;
+    for (const auto& c : cs) {
+        if (c.first < 0) neg.push_back({-c.first, c.second});
+        else if (c.first > 0) pos.push_back(c);
+    }
+    auto accumulate = [](const Groups& vs) {
+        Node out = constant(0.0f);
+        for (const auto& v : vs) {
+            Node cur = constant(0.0f);
+            for (const auto& n : v.second) cur = operation(Opcode::OP_ADD, cur, n);
+            out = operation(Opcode::OP_ADD, out, operation(Opcode::OP_MUL, cur, constant(v.first)));
+        }
+        return out;
+    };
+    return operation(Opcode::OP_SUB, accumulate(pos), accumulate(neg));
+}
+
+Node checkAffine(Opcode::Opcode op, const Node& a_, const Node& b_) {
+    if (op != Opcode::OP_ADD && op != Opcode::OP_SUB) return nullptr;
+    Affine a = asAffine(a_);
+    const Affine b = asAffine(b_);
+    bool overlap = false;
+    for (const auto& k : b) {
+        auto itr = a.find(k.first);
+        if (itr != a.end()) {
+            if (op == Opcode::OP_ADD) itr->second += k.second; else itr->second -= k.second;
+            overlap = true;
+        } else {
+            a.insert({k.first, op == Opcode::OP_ADD ? k.second : -k.second});
+        }
+    }
+    return overlap ? fromAffine(a) : nullptr;
+}
+
 Node operation(Opcode::Opcode op, Node lhs, Node rhs) {
     Tables& T = tables();
     if (T.simplify && Opcode::args(op) >= 1) {
         if (Node t = checkIdentity(op, lhs, rhs)) return t;
         if (Opcode::args(op) == 2) {
             if (Node t = checkCommutative(op, lhs, rhs)) return t;
+            if (Node t = checkAffine(op, lhs, rhs)) return t;
         }
     }
     // All-constant operands fold to a constant.
@@ -231,6 +323,7 @@ Node operation(Opcode::Opcode op, Node lhs, Node rhs) {
     const unsigned rank = std::max(lhs ? lhs->rank + 1 : 0u, rhs ? rhs->rank + 1 : 0u);
     Node n(new Tree::Tree_{op, uint8_t(agnostic ? Tree::FLAG_LOCATION_AGNOSTIC : 0), rank,
                            std::nanf(""), lhs, rhs});
+    n->serial = T.next_serial++;
     T.ops[k] = n;
     return n;
 }

@@ -161,7 +161,9 @@ template <> struct MatOf<3> { typedef Mat4 type; };
 ////////////////////////////////////////////////////////////////////////////////
 // Interval pass
 
-template <int DIM, bool ROOT, bool REMAP>
+// HEAT = true is the work-metering variant behind render*_heatmap: a separate instantiation so
+// that ordinary frames carry none of its registers or branches.
+template <int DIM, bool ROOT, bool REMAP, bool HEAT = false>
 __global__ void __launch_bounds__(kEvalThreads)
 k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
 {
@@ -379,6 +381,11 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
             st_tiles += n_alive;
             st_cells += (unsigned long long)n_alive * cells;
         }
+        // Work meter: cells this tile is charged with (context.cu:1622-1633).  The root tape is
+        // charged by its clause count: its chunked layout here carries JUMP cells the
+        // reference's contiguous copy does not.
+        unsigned heat_cells = 0;
+        if (HEAT && alive) heat_cells = (tape == 0) ? unsigned(a.n_root) : cells;
 
         // ---- tape push: backward mark & sweep (context.cu:323-458) ---------------------
         if (__any_sync(kFull, pushing)) {
@@ -504,6 +511,23 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                 st_ptiles += n_push;
                 st_pcells += (unsigned long long)n_push * bcells;
                 st_kept += warp_sum(pushed0 ? kept : 0u);
+            }
+            if (HEAT && pushed0) heat_cells += (tape == 0) ? unsigned(a.n_root) : bcells;   // context.cu:1815-1826
+        }
+        if (HEAT) {
+            // cells / px^2 onto every pixel of the footprint, in units of 1/4096 cell so that the
+            // sum is exact and order-independent; the warp spreads one tile at a time (coalesced rows)
+            const int px = a.heat_px;
+            const int size = int(tps) * px;
+            const unsigned long long units = (unsigned long long)heat_cells * unsigned(4096 / (px * px));
+            unsigned m = __ballot_sync(kFull, heat_cells != 0);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int bx = __shfl_sync(kFull, sx, src) * px, by = __shfl_sync(kFull, sy, src) * px;
+                const unsigned long long u = __shfl_sync(kFull, units, src);
+                for (int i = lane; i < px * px; i += 32)
+                    atomicAdd(&a.heat[size_t(by + i / px) * size + bx + i % px], u);
             }
         }
 
@@ -957,7 +981,7 @@ __device__ __forceinline__ float2 walk_float(TapeStream<REMAP>& ts, int tape, Sl
 }
 
 // 2D: one warp per surviving 8x8 tile, two pixels per lane (y and y + 4).
-template <bool REMAP>
+template <bool REMAP, bool HEAT = false>
 __global__ void __launch_bounds__(kFloatThreads)
 k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 {
@@ -1001,6 +1025,11 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
         const float2 r = walk_float(ts, tile.tape, slots, cells);
         if (r.y < 0.0f) a.image[px + (py + 4) * size] = 1;      // context.cu:951-962
         if (r.x < 0.0f) a.image[px + py * size] = 1;
+        if (HEAT) {                                             // work / 2 on each sample (context.cu:1979-1980)
+            const unsigned long long u = (unsigned long long)(tile.tape == 0 ? unsigned(a.n_root) : cells) * 2048u;
+            atomicAdd(&a.heat[px + size_t(py) * size], u);
+            atomicAdd(&a.heat[px + size_t(py + 4) * size], u);
+        }
         st_tiles += 1;
         st_cells += cells;
     }
@@ -1014,7 +1043,7 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 // Root tiles are issued highest-z first and children inherit that order, so the
 // list is roughly front-to-back and the per-lane early-out below (the
 // reference's, context.cu:852-864) culls most of what lies behind the surface.
-template <bool REMAP>
+template <bool REMAP, bool HEAT = false>
 __global__ void __launch_bounds__(kFloatThreads)
 k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
 {
@@ -1067,6 +1096,9 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
             // The higher sample wins when both are inside (context.cu:936-948)
             if (r.y < 0.0f) atomicMax(pix, pz + 2);
             else if (r.x < 0.0f) atomicMax(pix, pz);
+            if (HEAT)                                           // context.cu:1962
+                atomicAdd(&a.heat[px + size_t(py) * size],
+                          (unsigned long long)(tile.tape == 0 ? unsigned(a.n_root) : cells) * 4096u);
         }
         st_tiles += 1;
         st_cells += cells;
@@ -1240,6 +1272,27 @@ __global__ void k_begin_frame(FrameCtl* ctl, int32_t first_free)
     if (i == 0) ctl->tape_cursor = first_free;
 }
 
+// Brute-force frames (reference preload_tiles, context.cu:45-57): every 8x8 tile goes straight
+// to the float pass with the root tape.
+__global__ void k_preload_tiles(TileNode* __restrict__ tiles, int32_t count, int32_t* __restrict__ n_tiles)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        tiles[i].position = i;
+        tiles[i].tape = 0;
+        tiles[i].next = -1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_tiles = count;
+}
+
+// Work units -> the reference's heatmap value: cells per pixel over the clause count
+// (context.cu:2140-2144).
+__global__ void k_heat_finish(const unsigned long long* __restrict__ units, float* __restrict__ heat, long long n,
+                              int32_t n_clauses)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        heat[i] = __fdiv_rn(float(double(units[i]) / 4096.0), float(n_clauses));
+}
+
 ////////////////////////////////////////////////////////////////////////////////
 // Launch wrappers
 
@@ -1294,6 +1347,18 @@ void init_kernels(int max_smem_optin) {
     opt_in(k_eval_tiles<3, false, true>, max_smem_optin);
     opt_in(k_eval_root<2>, max_smem_optin);
     opt_in(k_eval_root<3>, max_smem_optin);
+    opt_in(k_eval_tiles<2, true, false, true>, max_smem_optin);
+    opt_in(k_eval_tiles<2, false, false, true>, max_smem_optin);
+    opt_in(k_eval_tiles<3, true, false, true>, max_smem_optin);
+    opt_in(k_eval_tiles<3, false, false, true>, max_smem_optin);
+    opt_in(k_eval_tiles<2, true, true, true>, max_smem_optin);
+    opt_in(k_eval_tiles<2, false, true, true>, max_smem_optin);
+    opt_in(k_eval_tiles<3, true, true, true>, max_smem_optin);
+    opt_in(k_eval_tiles<3, false, true, true>, max_smem_optin);
+    opt_in(k_eval_pixels<false, true>, max_smem_optin);
+    opt_in(k_eval_voxels<false, true>, max_smem_optin);
+    opt_in(k_eval_pixels<true, true>, max_smem_optin);
+    opt_in(k_eval_voxels<true, true>, max_smem_optin);
     opt_in(k_eval_pixels<false>, max_smem_optin);
     opt_in(k_eval_voxels<false>, max_smem_optin);
     opt_in(k_normals<false>, max_smem_optin);
@@ -1307,7 +1372,10 @@ static void launch_eval_tiles_t(const EvalTilesArgs& a, const void* mat, int gri
     const bool local = use_remap(a.n_slots);
     const size_t smem = walk_smem(a.n_rows, local);
     const auto& m = *static_cast<const typename MatOf<DIM>::type*>(mat);
-    if (local) k_eval_tiles<DIM, ROOT, true><<<grid, kEvalThreads, smem, s>>>(a, m);
+    if (a.heat) {
+        if (local) k_eval_tiles<DIM, ROOT, true, true><<<grid, kEvalThreads, smem, s>>>(a, m);
+        else k_eval_tiles<DIM, ROOT, false, true><<<grid, kEvalThreads, smem, s>>>(a, m);
+    } else if (local) k_eval_tiles<DIM, ROOT, true><<<grid, kEvalThreads, smem, s>>>(a, m);
     else k_eval_tiles<DIM, ROOT, false><<<grid, kEvalThreads, smem, s>>>(a, m);
 }
 
@@ -1342,14 +1410,20 @@ void launch_upsample_filled(int dim, const int32_t* prev, int32_t* image, int si
 void launch_eval_pixels(const EvalVoxelsArgs& a, const Mat3& mat, int grid, cudaStream_t s) {
     const bool local = use_remap(a.n_slots);
     const size_t smem = walk_smem(a.n_rows, local, kFloatWarps);
-    if (local) k_eval_pixels<true><<<grid, kFloatThreads, smem, s>>>(a, mat);
+    if (a.heat) {
+        if (local) k_eval_pixels<true, true><<<grid, kFloatThreads, smem, s>>>(a, mat);
+        else k_eval_pixels<false, true><<<grid, kFloatThreads, smem, s>>>(a, mat);
+    } else if (local) k_eval_pixels<true><<<grid, kFloatThreads, smem, s>>>(a, mat);
     else k_eval_pixels<false><<<grid, kFloatThreads, smem, s>>>(a, mat);
 }
 
 void launch_eval_voxels(const EvalVoxelsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
     const bool local = use_remap(a.n_slots);
     const size_t smem = walk_smem(a.n_rows, local, kFloatWarps);
-    if (local) k_eval_voxels<true><<<grid, kFloatThreads, smem, s>>>(a, mat);
+    if (a.heat) {
+        if (local) k_eval_voxels<true, true><<<grid, kFloatThreads, smem, s>>>(a, mat);
+        else k_eval_voxels<false, true><<<grid, kFloatThreads, smem, s>>>(a, mat);
+    } else if (local) k_eval_voxels<true><<<grid, kFloatThreads, smem, s>>>(a, mat);
     else k_eval_voxels<false><<<grid, kFloatThreads, smem, s>>>(a, mat);
 }
 
@@ -1358,6 +1432,15 @@ void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_
     const size_t smem = normals_smem(a.n_slots, local);
     if (local) k_normals<true><<<grid, kEvalThreads, smem, s>>>(a, mat);
     else k_normals<false><<<grid, kEvalThreads, smem, s>>>(a, mat);
+}
+
+void launch_preload_tiles(TileNode* tiles, int32_t count, int32_t* n_tiles, int grid, cudaStream_t s) {
+    k_preload_tiles<<<grid, 256, 0, s>>>(tiles, count, n_tiles);
+}
+
+void launch_heat_finish(const unsigned long long* units, float* heat, long long n, int32_t n_clauses, int grid,
+                        cudaStream_t s) {
+    k_heat_finish<<<grid, 256, 0, s>>>(units, heat, n, n_clauses);
 }
 
 void launch_begin_frame(FrameCtl* ctl, int32_t first_free, cudaStream_t s) {

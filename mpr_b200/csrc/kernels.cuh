@@ -38,6 +38,10 @@ struct EvalTilesArgs {
     int32_t n_slots;          // slot ids used by the root tape, +1
     int32_t n_rows;           // shared-memory value rows per warp (walk_rows(n_slots))
     float z;                  // 2D only: the constant z
+    // Work meter (render*_heatmap, context.cu:1513-2340); null on ordinary frames.
+    unsigned long long* heat; // S x S accumulators, units of 1/4096 cell
+    int32_t heat_px;          // this level's tile edge in pixels
+    int32_t n_root;           // clauses of the root tape (its walk is charged without the layout's JUMPs)
 };
 
 // One clause of a root tape in SSA / dependency-level order (built on the host per Tape).
@@ -102,6 +106,8 @@ struct EvalVoxelsArgs {
     int32_t n_slots;
     int32_t n_rows;           // shared-memory value rows per warp (walk_rows(n_slots))
     float z;
+    unsigned long long* heat; // work meter, see EvalTilesArgs
+    int32_t n_root;
 };
 
 struct NormalsArgs {
@@ -122,6 +128,9 @@ struct NormalsArgs {
 };
 
 void init_kernels(int max_smem_optin);
+void launch_preload_tiles(TileNode* tiles, int32_t count, int32_t* n_tiles, int grid, cudaStream_t s);
+void launch_heat_finish(const unsigned long long* units, float* heat, long long n, int32_t n_clauses, int grid,
+                        cudaStream_t s);
 void launch_begin_frame(FrameCtl* ctl, int32_t first_free, cudaStream_t s);
 void launch_eval_tiles(int dim, bool root, const EvalTilesArgs& a, const void* mat, int grid, cudaStream_t s);
 void launch_eval_root(int dim, const EvalRootArgs& a, const void* mat, cudaStream_t s);

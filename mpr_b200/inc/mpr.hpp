@@ -8,6 +8,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <memory>
 
@@ -36,6 +37,32 @@ namespace libfive { class Tree; }
 #else
 #define NUM_SUBTAPES 640000
 #endif
+#endif
+
+// inc/util.hpp:19-41.  CUDA_MALLOC / CUDA_FREE go through the C ABI, so host-only drivers need no
+// CUDA toolkit; CUDA_CHECK exists only where the CUDA runtime header does (brute.cu, gui/tex.cu).
+#ifndef CUDA_MALLOC
+namespace mpr { namespace detail {
+template <typename T> inline T* managed_checked(size_t count, const char* file, int line) {
+    void* p = nullptr;
+    if (mprb_malloc_managed(sizeof(T) * count, &p) != 0) {
+        fprintf(stderr, "Error: %s %s %d\n", mprb_last_error(), file, line);
+        exit(1);
+    }
+    return static_cast<T*>(p);
+}
+} }
+#define CUDA_MALLOC(T, c) mpr::detail::managed_checked<T>(c, __FILE__, __LINE__)
+#define CUDA_FREE(c) mprb_free_device((void*)(c))
+#endif
+#if defined(__CUDACC__) && !defined(CUDA_CHECK)
+#define CUDA_CHECK(f) { mpr_gpu_check((f), __FILE__, __LINE__); }
+inline void mpr_gpu_check(cudaError_t code, const char* file, int line) {
+    if (code != cudaSuccess) {
+        fprintf(stderr, "Error: %s %s %d\n", cudaGetErrorString(code), file, line);
+        exit(code);
+    }
+}
 #endif
 
 namespace mpr {
@@ -111,6 +138,23 @@ struct Context {
         refresh();
     }
 
+    void render2D_brute(const Tape& tape, const Eigen::Matrix3f& mat, const float z = 0.0f) {
+        detail::check(mprb_render2d_brute(handle.get(), tape.handle.get(), mat.data(), z), "render2D_brute");
+        refresh();
+    }
+    Ptr<float[]> render2D_heatmap(const Tape& tape, const Eigen::Matrix3f& mat, const float z = 0.0f) {
+        float* h = nullptr;
+        detail::check(mprb_render2d_heatmap(handle.get(), tape.handle.get(), mat.data(), z, &h), "render2D_heatmap");
+        refresh();
+        return Ptr<float[]>(h);
+    }
+    Ptr<float[]> render3D_heatmap(const Tape& tape, const Eigen::Matrix4f& mat) {
+        float* h = nullptr;
+        detail::check(mprb_render3d_heatmap(handle.get(), tape.handle.get(), mat.data(), &h), "render3D_heatmap");
+        refresh();
+        return Ptr<float[]>(h);
+    }
+
     int32_t image_size_px;
     Ptr<uint64_t[]> tape_data;
     Ptr<int32_t> tape_index;
@@ -134,6 +178,52 @@ private:
             stages[i].tiles = detail::borrowed<TileNode[]>(reinterpret_cast<TileNode*>(b.tiles[i]));
             stages[i].tile_array_size = size_t(b.tile_array_size[i]);
         }
+    }
+};
+
+// inc/effects.hpp
+struct Effects {
+    Effects() {
+        // Same draws, same order as the reference constructor (src/effects.cu:229-250): the sample
+        // sets depend on the process-wide rand() state exactly as they do there.
+        float kernel[64 * 3], rvecs[256 * 3];                       // column-major 64x3 / 256x3
+        for (unsigned i = 0; i < 64; ++i) {
+            float v[3] = {2.0f * ((float)(rand()) / (float)(RAND_MAX) - 0.5f),
+                          2.0f * ((float)(rand()) / (float)(RAND_MAX) - 0.5f),
+                          (float)(rand()) / (float)(RAND_MAX)};
+            const float n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            float scale = float(i) / float(64 - 1);
+            scale = (scale * scale) * 0.9f + 0.1f;
+            for (int k = 0; k < 3; ++k) kernel[k * 64 + i] = v[k] / n * scale;
+        }
+        for (unsigned i = 0; i < 256; ++i) {
+            float v[3] = {2.0f * ((float)(rand()) / (float)(RAND_MAX) - 0.5f),
+                          2.0f * ((float)(rand()) / (float)(RAND_MAX) - 0.5f), 0.0f};
+            const float n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            for (int k = 0; k < 3; ++k) rvecs[k * 256 + i] = v[k] / n;
+        }
+        mprb_effects* fx = nullptr;
+        detail::check(mprb_effects_create(kernel, rvecs, &fx), "mprb_effects_create");
+        handle.reset(fx, [](mprb_effects* p) { mprb_effects_destroy(p); });
+    }
+    Ptr<int32_t[]> tmp;
+    Ptr<int32_t[]> image;
+    void drawSSAO(const Context& ctx) {
+        detail::check(mprb_effects_draw_ssao(handle.get(), ctx.handle.get()), "drawSSAO");
+        refresh();
+    }
+    void drawShaded(const Context& ctx) {
+        detail::check(mprb_effects_draw_shaded(handle.get(), ctx.handle.get()), "drawShaded");
+        refresh();
+    }
+    std::shared_ptr<mprb_effects> handle;
+
+private:
+    void refresh() {
+        int32_t *i = nullptr, *t = nullptr;
+        detail::check(mprb_effects_buffers(handle.get(), &i, &t), "mprb_effects_buffers");
+        image = detail::borrowed<int32_t[]>(i);
+        tmp = detail::borrowed<int32_t[]>(t);
     }
 };
 

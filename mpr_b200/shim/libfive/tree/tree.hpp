@@ -34,6 +34,7 @@ public:
         float value;
         std::shared_ptr<Tree_> lhs;
         std::shared_ptr<Tree_> rhs;
+        uint64_t serial = 0;        // creation order; stands in for libfive's pointer-ordered maps
         ~Tree_();
     };
     typedef const Tree_* Id;

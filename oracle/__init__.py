@@ -45,6 +45,10 @@ def oracle_lib():
         L.mpro_destroy.argtypes = [vp]
         L.mpro_render2d.argtypes = [vp, vp, C.c_int32, vp, C.c_float, C.c_int]
         L.mpro_render3d.argtypes = [vp, vp, C.c_int32, vp, C.c_int]
+        L.mpro_render2d_brute.argtypes = [vp, vp, C.c_int32, vp, C.c_float, C.c_int]
+        L.mpro_set_heat.argtypes = [vp, C.c_int]
+        L.mpro_heat.argtypes = [vp]
+        L.mpro_heat.restype = vp
         for name, rt in [("mpro_filled", vp), ("mpro_tiles", vp)]:
             getattr(L, name).argtypes = [vp, C.c_int]
             getattr(L, name).restype = rt
@@ -66,6 +70,9 @@ def oracle_lib():
         L.mpro_tape_hashes.argtypes = [vp, vp, C.c_int64, vp, vp]
         L.mpro_tape_flatten.argtypes = [vp, C.c_int32, vp, C.c_int32]
         L.mpro_tape_flatten.restype = C.c_int32
+        L.mpro_fx_ssao.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
+        L.mpro_fx_shaded.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
+        L.mpro_fx_ssao.restype = L.mpro_fx_shaded.restype = None
         _oracle = L
     return _oracle
 
@@ -160,6 +167,30 @@ class CpuOracle(_Base):
         m = _mat(view_matrix_3d() if mat is None else mat, 4)
         self.L.mpro_render3d(self.h, cells.ctypes.data, cells.size, m.ctypes.data, threads)
 
+    def render2D_brute(self, cells, mat=None, z=0.0, threads=0):
+        cells = np.ascontiguousarray(cells, dtype=np.uint64)
+        m = _mat(np.eye(3) if mat is None else mat, 3)
+        self.L.mpro_render2d_brute(self.h, cells.ctypes.data, cells.size, m.ctypes.data, z, threads)
+
+    def _heatmap(self, render, cells, *args):
+        """render*_heatmap (reference context.cu:1984-2340): amortised cells walked per pixel,
+        divided by the clause count of the tape."""
+        self.L.mpro_set_heat(self.h, 1)
+        try:
+            render(cells, *args)
+            units = _as_array(self.L.mpro_heat(self.h), (self.size, self.size), np.uint64).copy()
+        finally:
+            self.L.mpro_set_heat(self.h, 0)
+        return units
+
+    def render2D_heatmap(self, cells, mat=None, z=0.0):
+        units = self._heatmap(self.render2D, cells, mat, z)
+        return heat_from_units(units, len(cells)), units
+
+    def render3D_heatmap(self, cells, mat=None):
+        units = self._heatmap(self.render3D, cells, mat)
+        return heat_from_units(units, len(cells)), units
+
     def _filled_ptr(self, s): return self.L.mpro_filled(self.h, s)
     def _tiles_ptr(self, s): return self.L.mpro_tiles(self.h, s)
     def _tile_count(self, s): return int(self.L.mpro_tile_count(self.h, s))
@@ -168,6 +199,11 @@ class CpuOracle(_Base):
     def tape_index(self): return int(self.L.mpro_tape_index(self.h))
     def work(self): return int(self.L.mpro_work_interval(self.h)), int(self.L.mpro_work_float(self.h))
     def max_threads(self): return int(self.L.mpro_max_threads())
+
+
+def heat_from_units(units, n_cells):
+    """Integer work units (1/4096 cell) -> the reference's float heatmap value."""
+    return ((units.astype(np.float64) / 4096.0).astype(np.float32) / np.float32(n_cells - 2)).astype(np.float32)
 
 
 def ref_available() -> bool:
@@ -205,6 +241,9 @@ def ref_lib():
         L.ref_normals.restype = vp
         L.ref_num_subtapes.restype = C.c_int64
         L.ref_download.argtypes = [vp, vp, vp]
+        L.ref_render2d_brute.argtypes = [vp, vp, vp, C.c_float]
+        L.ref_render2d_heatmap.argtypes = [vp, vp, vp, C.c_float, vp]
+        L.ref_render3d_heatmap.argtypes = [vp, vp, vp, vp]
         _ref = L
     return _ref
 
@@ -250,6 +289,25 @@ class RefGpu(_Base):
         self.L.ref_render3d(self.h, self.tape(cells), m.ctypes.data)
         self._dim = 3
 
+    def render2D_brute(self, cells, mat=None, z=0.0):
+        m = _mat(np.eye(3) if mat is None else mat, 3)
+        self.L.ref_render2d_brute(self.h, self.tape(cells), m.ctypes.data, z)
+        self._dim = 2
+
+    def render2D_heatmap(self, cells, mat=None, z=0.0):
+        m = _mat(np.eye(3) if mat is None else mat, 3)
+        heat = np.zeros((self.size, self.size), dtype=np.float32)
+        self.L.ref_render2d_heatmap(self.h, self.tape(cells), m.ctypes.data, z, heat.ctypes.data)
+        self._dim = 2
+        return heat
+
+    def render3D_heatmap(self, cells, mat=None):
+        m = _mat(view_matrix_3d() if mat is None else mat, 4)
+        heat = np.zeros((self.size, self.size), dtype=np.float32)
+        self.L.ref_render3d_heatmap(self.h, self.tape(cells), m.ctypes.data, heat.ctypes.data)
+        self._dim = 3
+        return heat
+
     def _filled_ptr(self, s): return self.L.ref_filled(self.h, s)
     def _tiles_ptr(self, s): return self.L.ref_tiles(self.h, s)
 
@@ -284,3 +342,21 @@ class RefGpu(_Base):
     def _normals_ptr(self): return self.L.ref_normals(self.h)
     def _arena_ptr(self): return self.L.ref_tape_data(self.h)
     def tape_index(self): return int(self.L.ref_tape_index(self.h))
+
+
+def effects(depth, normals, kernel, rvecs, shaded=False):
+    """CPU restatement of mpr::Effects::drawSSAO / drawShaded (reference src/effects.cu:253-297) on a
+    depth image + packed normals; kernel 64x3 and rvecs 256x3 as Fortran-ordered float32.  Returns
+    (image, tmp)."""
+    L = oracle_lib()
+    depth = np.ascontiguousarray(depth, dtype=np.int32)
+    normals = np.ascontiguousarray(normals, dtype=np.uint32)
+    kernel = np.asfortranarray(kernel, dtype=np.float32)
+    rvecs = np.asfortranarray(rvecs, dtype=np.float32)
+    size = depth.shape[0]
+    tmp = np.zeros((size, size), dtype=np.int32)
+    image = np.zeros((size, size), dtype=np.int32)
+    fn = L.mpro_fx_shaded if shaded else L.mpro_fx_ssao
+    fn(depth.ctypes.data, normals.ctypes.data, kernel.ctypes.data, rvecs.ctypes.data, size,
+       tmp.ctypes.data, image.ctypes.data)
+    return image, tmp

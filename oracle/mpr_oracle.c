@@ -61,6 +61,7 @@ typedef struct {
     /* work counters of the last frame */
     uint64_t work_interval;   /* interval clause evaluations */
     uint64_t work_float;      /* float voxel*clause evaluations */
+    uint64_t* heat;           /* optional S*S work meter, units of 1/4096 cell (render*_heatmap) */
 } oracle_ctx;
 
 /* ---- clause fields (reference inc/clause.hpp:18-23) ------------------------------- */
@@ -231,6 +232,31 @@ static inline void image_max(int32_t* p, int32_t v) {
 }
 
 /* eval_tiles_i for one tile (context.cu:188-459).  Returns clauses evaluated. */
+/* Work meter of the *_heatmap variants (context.cu:1622-1633, :1815-1826): a tile spreads the
+ * cells it walked (JUMP cells included, as `work++` sits before the switch there) evenly over
+ * its footprint: cells / px^2 per pixel.  Kept in integer units of 1/4096 cell so that the sum
+ * does not depend on the order of the additions. */
+static void heat_tile(oracle_ctx* c, int tps, int32_t position, unsigned cells) {
+    if (!c->heat || !cells) return;
+    const int px = c->size / tps;
+    const uint64_t units = (uint64_t)cells * (uint64_t)(4096 / (px * px));
+    const int x0 = (position % tps) * px, y0 = ((position / tps) % tps) * px;
+    for (int y = 0; y < px; ++y)
+        for (int x = 0; x < px; ++x)
+            __atomic_fetch_add(&c->heat[(size_t)(y0 + y) * c->size + x0 + x], units, __ATOMIC_RELAXED);
+}
+/* cells a forward walk of this tape visits before the end cell, JUMPs included */
+static unsigned tape_cells(const uint64_t* tape_data, int32_t tape) {
+    const uint64_t* data = &tape_data[tape];
+    unsigned n = 0;
+    for (;;) {
+        const uint64_t d = *++data;
+        if (!c_op(d)) return n;
+        ++n;
+        if (c_op(d) == OP_JUMP) data += c_jump(d);
+    }
+}
+
 static unsigned eval_tile_interval(oracle_ctx* c, int dim, int32_t* image, int tps, tile_t* tile,
                                    const ival values[3])
 {
@@ -250,11 +276,14 @@ static unsigned eval_tile_interval(oracle_ctx* c, int dim, int32_t* image, int t
     int choice_index = 0;
     int has_any_choice = 0;
     unsigned work = 0;
+    unsigned hcells = 0;                   /* work as the heatmap variant counts it */
+    const int32_t hpos = tile->position;
 
     for (;;) {                                                                /* :223-287 */
         const uint64_t d = *++data;
         const unsigned op = c_op(d);
         if (!op) break;
+        ++hcells;
         if (op == OP_JUMP) { data += c_jump(d); continue; }
         ++work;
         const ival lhs = slots[c_lhs(d)], rhs = slots[c_rhs(d)];
@@ -300,6 +329,8 @@ static unsigned eval_tile_interval(oracle_ctx* c, int dim, int32_t* image, int t
     }
 
     const unsigned i_out = c_out(*data);                                      /* :290 */
+    heat_tile(c, tps, hpos, hcells);                                          /* :1622-1633 */
+    hcells = 0;
     int x, y, z, w;
     unpack(tile->position, tps, &x, &y, &z, &w);
     if (slots[i_out].lo > 0.0f) { tile->position = -1; return work; }         /* empty :293-296 */
@@ -328,6 +359,7 @@ static unsigned eval_tile_interval(oracle_ctx* c, int dim, int32_t* image, int t
         uint64_t d = *--data;
         const unsigned op = c_op(d);
         if (!op) break;
+        ++hcells;
         if (op == OP_JUMP) { data += c_jump(d); continue; }
         const int has_choice = op >= OP_MIN_LI && op <= OP_MAX_LR;
         choice_index -= has_choice;
@@ -338,10 +370,10 @@ static unsigned eval_tile_interval(oracle_ctx* c, int dim, int32_t* image, int t
         --out_offset;
         if (out_offset == 0) {
             const int32_t prev_index = out_index;
-            if (__atomic_load_n(&c->tape_index, __ATOMIC_RELAXED) >= cap) return work;
+            if (__atomic_load_n(&c->tape_index, __ATOMIC_RELAXED) >= cap) { heat_tile(c, tps, hpos, hcells); return work; }
             out_index = claim_chunk(c);
             out_offset = CHUNK;
-            if ((int64_t)out_index + out_offset >= cap) return work;
+            if ((int64_t)out_index + out_offset >= cap) { heat_tile(c, tps, hpos, hcells); return work; }
             --out_offset;
             const int32_t delta = prev_index - (out_index + out_offset);
             tape_data[out_index + out_offset] = (uint64_t)OP_JUMP | ((uint64_t)(uint32_t)delta << 32);
@@ -367,6 +399,7 @@ static unsigned eval_tile_interval(oracle_ctx* c, int dim, int32_t* image, int t
         }
         tape_data[out_index + out_offset] = d;
     }
+    heat_tile(c, tps, hpos, hcells);                                          /* :1815-1826 */
     out_offset--;
     tape_data[out_index + out_offset] = *data;
     tile->tape = out_index + out_offset;
@@ -509,7 +542,8 @@ static void ensure_tiles(oracle_ctx* c, int stage, size_t n) {
     }
 }
 
-static void render(oracle_ctx* c, int dim, const uint64_t* tape, int32_t n_cells, const float* mat, float zc, int threads)
+static void render(oracle_ctx* c, int dim, const uint64_t* tape, int32_t n_cells, const float* mat, float zc, int threads,
+                   int brute)
 {
     const int S = c->size;
     (void)threads;
@@ -523,6 +557,7 @@ static void render(oracle_ctx* c, int dim, const uint64_t* tape, int32_t n_cells
         memset(c->filled[i], 0, sizeof(int32_t) * side * side);
     }
     memset(c->normals, 0, sizeof(uint32_t) * (size_t)S * S);
+    if (c->heat) memset(c->heat, 0, sizeof(uint64_t) * (size_t)S * S);
     uint64_t work_i = 0, work_f = 0;
 
     const int n_levels = dim == 3 ? 3 : 2;
@@ -531,14 +566,22 @@ static void render(oracle_ctx* c, int dim, const uint64_t* tape, int32_t n_cells
     const int split = dim == 3 ? 4 : 8;
 
     size_t count = 1;
-    for (int i = 0; i < dim; ++i) count *= (size_t)(S / 64);
-    ensure_tiles(c, 0, count);
-    for (size_t i = 0; i < count; ++i) {                                      /* preload_tiles :45 */
+    if (brute) {                                                              /* render2D_brute :1461-1508 */
+        count = (size_t)(S / 8) * (S / 8);
+        ensure_tiles(c, 3, count);
+        for (size_t i = 0; i < count; ++i) {
+            c->tiles[3][i].position = (int32_t)i; c->tiles[3][i].tape = 0; c->tiles[3][i].next = -1;
+        }
+        c->tile_count[3] = count;
+    }
+    for (int i = 0; i < dim && !brute; ++i) count *= (size_t)(S / 64);
+    if (!brute) ensure_tiles(c, 0, count);
+    for (size_t i = 0; i < count && !brute; ++i) {                            /* preload_tiles :45 */
         c->tiles[0][i].position = (int32_t)i; c->tiles[0][i].tape = 0; c->tiles[0][i].next = -1;
     }
-    c->tile_count[0] = count;
+    if (!brute) c->tile_count[0] = count;
 
-    for (int l = 0; l < n_levels; ++l) {
+    for (int l = 0; l < n_levels && !brute; ++l) {
         const int st = stage_of[l];
         const int tps = S / px_of[l];
         tile_t* tiles = c->tiles[st];
@@ -622,11 +665,14 @@ static void render(oracle_ctx* c, int dim, const uint64_t* tape, int32_t n_cells
             fesetround(FE_TONEAREST);
             int tx, ty, tz, tw; unpack(tiles[i].position, tps, &tx, &ty, &tz, &tw);
             unsigned work = 0;
+            const uint64_t hcells = c->heat ? tape_cells(c->arena, tiles[i].tape) : 0;
             for (int lane = 0; lane < 32; ++lane) {
                 if (dim == 3) {
                     const int px = tx * 4 + lane % 4, py = ty * 4 + (lane / 4) % 4, pz = tz * 4 + lane / 16;
                     int32_t* pix = &image[px + py * S];
                     if (__atomic_load_n(pix, __ATOMIC_RELAXED) >= pz + 2) continue;      /* :861 */
+                    if (c->heat)                                                           /* :1962 */
+                        __atomic_fetch_add(&c->heat[px + (size_t)py * S], hcells * 4096u, __ATOMIC_RELAXED);
                     const float fx = sample_coord(px, recip), fy = sample_coord(py, recip);
                     float val[2];
                     for (int k = 0; k < 2; ++k) {
@@ -642,6 +688,10 @@ static void render(oracle_ctx* c, int dim, const uint64_t* tape, int32_t n_cells
                 } else {
                     const int px = tx * 8 + lane % 8, py = ty * 8 + lane / 8;
                     const float fx = sample_coord(px, recip);
+                    if (c->heat) {                                                         /* :1979-1980 */
+                        c->heat[px + (size_t)py * S] += hcells * 2048u;
+                        c->heat[px + (size_t)(py + 4) * S] += hcells * 2048u;
+                    }
                     for (int k = 0; k < 2; ++k) {
                         const float fy = sample_coord(py + 4 * k, recip);
                         const float w = dot2(mat[2], fx, mat[5], fy, mat[8]);
@@ -712,13 +762,16 @@ oracle_ctx* mpro_create(int size, int64_t num_subtapes) {
 void mpro_destroy(oracle_ctx* c) {
     if (!c) return;
     for (int i = 0; i < 4; ++i) { free(c->filled[i]); free(c->tiles[i]); }
-    free(c->normals); free(c->arena); free(c);
+    free(c->normals); free(c->arena); free(c->heat); free(c);
 }
 void mpro_render2d(oracle_ctx* c, const uint64_t* tape, int32_t n, const float* mat3, float z, int threads) {
-    render(c, 2, tape, n, mat3, z, threads);
+    render(c, 2, tape, n, mat3, z, threads, 0);
 }
 void mpro_render3d(oracle_ctx* c, const uint64_t* tape, int32_t n, const float* mat4, int threads) {
-    render(c, 3, tape, n, mat4, 0.0f, threads);
+    render(c, 3, tape, n, mat4, 0.0f, threads, 0);
+}
+void mpro_render2d_brute(oracle_ctx* c, const uint64_t* tape, int32_t n, const float* mat3, float z, int threads) {
+    render(c, 2, tape, n, mat3, z, threads, 1);
 }
 int32_t* mpro_filled(oracle_ctx* c, int stage) { return c->filled[stage]; }
 tile_t* mpro_tiles(oracle_ctx* c, int stage) { return c->tiles[stage]; }
@@ -726,6 +779,14 @@ uint64_t mpro_tile_count(oracle_ctx* c, int stage) { return c->tile_count[stage]
 uint64_t* mpro_arena(oracle_ctx* c) { return c->arena; }
 int32_t mpro_tape_index(oracle_ctx* c) { return c->tape_index; }
 uint32_t* mpro_normals(oracle_ctx* c) { return c->normals; }
+/* Switches the work meter on (context.cu:1984-2340, render2D_heatmap / render3D_heatmap): after
+ * the next render mpro_heat() holds, per pixel, 4096 x the amortised cells walked; dividing by
+ * 4096 * (tape length - 2) gives the reference's heatmap value. */
+void mpro_set_heat(oracle_ctx* c, int on) {
+    if (on && !c->heat) c->heat = (uint64_t*)calloc((size_t)c->size * c->size, sizeof(uint64_t));
+    if (!on && c->heat) { free(c->heat); c->heat = NULL; }
+}
+uint64_t* mpro_heat(oracle_ctx* c) { return c->heat; }
 uint64_t mpro_work_interval(oracle_ctx* c) { return c->work_interval; }
 uint64_t mpro_work_float(oracle_ctx* c) { return c->work_float; }
 int mpro_max_threads(void) {
@@ -827,4 +888,151 @@ void mpro_eval_points(const uint64_t* tape, const float* xyz, int64_t n, float* 
         unsigned work = 0;
         out[i] = eval_tape_float(tape, 0, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &work);
     }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Post-effects (reference src/effects.cu).  PARITY UNPINNED: effects.cu needs Eigen in device
+ * code and cannot be compiled here, so these follow the source text only; floating point is
+ * evaluated operation by operation in round-to-nearest without contraction.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { float x, y, z; } fx_v3;
+static fx_v3 fx_mk(float x, float y, float z) { fx_v3 v = {x, y, z}; return v; }
+static float fx_dot(fx_v3 a, fx_v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static fx_v3 fx_norm(fx_v3 a) {                    /* Eigen normalized(): untouched when the norm is 0 */
+    float z = fx_dot(a, a);
+    if (z > 0.0f) { float n = sqrtf(z); return fx_mk(a.x / n, a.y / n, a.z / n); }
+    return a;
+}
+static float fx_ndc(float p, int size) { return 2.0f * ((p + 0.5f) / (float)size - 0.5f); }
+/* CUDA float -> unsigned conversion: saturating, NaN -> 0 */
+static unsigned fx_f2u(float f) {
+    if (!(f > 0.0f)) return 0u;
+    if (f >= 4294967296.0f) return 0xffffffffu;
+    return (unsigned)f;
+}
+static int32_t fx_f2i(float f) {                   /* CUDA float -> int: saturating, NaN -> 0 */
+    if (f != f) return 0;
+    if (f >= 2147483648.0f) return 0x7fffffff;
+    if (f <= -2147483648.0f) return (int32_t)0x80000000;
+    return (int32_t)f;
+}
+static fx_v3 fx_unpack_normal(uint32_t n) {
+    return fx_norm(fx_mk((float)(n & 0xFF) - 128.0f, (float)((n >> 8) & 0xFF) - 128.0f,
+                         (float)((n >> 16) & 0xFF) - 128.0f));
+}
+
+/* draw_ssao, effects.cu:17-89.  kernel 64x3 / rvecs 256x3 column-major. */
+void mpro_fx_draw_ssao(const int32_t* depth, const uint32_t* norm, const float* kernel, const float* rvecs,
+                       int size, int32_t* output) {
+    const float RADIUS = 0.1f;
+    #pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < size; ++y)
+        for (int x = 0; x < size; ++x) {
+            const int h = depth[x + y * size];
+            if (!h) continue;
+            const fx_v3 pos = fx_mk(fx_ndc((float)x, size), fx_ndc((float)y, size), fx_ndc((float)h, size));
+            const fx_v3 normal = fx_unpack_normal(norm[x + y * size]);
+            const int ri = (x % 16) * 16 + (y % 16);          /* threadIdx % 16 with 16x16 blocks */
+            const fx_v3 rvec = fx_mk(rvecs[ri], rvecs[256 + ri], rvecs[512 + ri]);
+            const float rn = fx_dot(rvec, normal);
+            const fx_v3 tangent = fx_norm(fx_mk(rvec.x - normal.x * rn, rvec.y - normal.y * rn, rvec.z - normal.z * rn));
+            const fx_v3 bitangent = fx_mk(normal.y * tangent.z - normal.z * tangent.y,
+                                          normal.z * tangent.x - normal.x * tangent.z,
+                                          normal.x * tangent.y - normal.y * tangent.x);
+            float occlusion = 0.0f;
+            for (int i = 0; i < 64; ++i) {
+                const fx_v3 k = fx_mk(kernel[i], kernel[64 + i], kernel[128 + i]);
+                const fx_v3 r = fx_mk(tangent.x * k.x + bitangent.x * k.y + normal.x * k.z,
+                                      tangent.y * k.x + bitangent.y * k.y + normal.y * k.z,
+                                      tangent.z * k.x + bitangent.z * k.y + normal.z * k.z);
+                const fx_v3 sp = fx_mk(r.x * RADIUS + pos.x, r.y * RADIUS + pos.y, r.z * RADIUS + pos.z);
+                const unsigned px = fx_f2u((sp.x / 2.0f + 0.5f) * (float)size);
+                const unsigned py = fx_f2u((sp.y / 2.0f + 0.5f) * (float)size);
+                const unsigned actual_h = (px < (unsigned)size && py < (unsigned)size) ? (unsigned)depth[px + py * size] : 0u;
+                const float actual_z = 2.0f * (((float)actual_h + 0.5f) / (float)size - 0.5f);
+                const float dz = fabsf(sp.z - actual_z);
+                if (dz < RADIUS) {
+                    occlusion += (sp.z <= actual_z) ? 1.0f : 0.0f;
+                } else if (dz < RADIUS * 2.0f) {
+                    if (sp.z <= actual_z) {
+                        const float t = (RADIUS - (dz - RADIUS)) / RADIUS;
+                        occlusion += t * t;                    /* powf(t, 2.0f) */
+                    }
+                }
+            }
+            occlusion = (float)(1.0 - (double)(occlusion / 64.0f));
+            output[x + y * size] = (uint8_t)fx_f2u(occlusion * 255.0f);
+        }
+}
+
+/* blur_ssao, effects.cu:93-155 (including the origin-relative second loop). */
+void mpro_fx_blur_ssao(const int32_t* image, const int32_t* ssao, int size, int32_t* output) {
+    #pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < size; ++y)
+        for (int x = 0; x < size; ++x) {
+            float best = 1000000.0f, value = 0.0f;
+            for (unsigned q = 0; q < 4; ++q) {
+                const int xmin = (q & 1) ? 0 : -2, ymin = (q & 2) ? 0 : -2;
+                float sum = 0.0f, count = 0.0f;
+                for (int i = 0; i <= 2; ++i)
+                    for (int j = 0; j <= 2; ++j) {
+                        const int tx = x + xmin + i, ty = y + ymin + j;
+                        if (tx >= 0 && tx < size && ty >= 0 && ty < size && image[tx + ty * size]) {
+                            sum += (float)ssao[tx + ty * size];
+                            count += 1.0f;
+                        }
+                    }
+                const float mean = sum / count;
+                float stdev = 0.0f;
+                for (int i = 0; i <= 2; ++i)
+                    for (int j = 0; j <= 2; ++j) {
+                        const int tx = xmin + i, ty = ymin + j;
+                        if (tx >= 0 && tx < size && ty >= 0 && ty < size && image[tx + ty * size]) {
+                            const float d = mean - (float)ssao[tx + ty * size];
+                            stdev += d * d;
+                        }
+                    }
+                stdev /= count - 1.0f;
+                stdev = sqrtf(stdev);
+                if (stdev < best) { best = stdev; value = mean; }
+            }
+            output[x + y * size] = fx_f2i(value);
+        }
+}
+
+/* draw_shaded, effects.cu:159-225. */
+void mpro_fx_draw_shaded(const int32_t* depth, const uint32_t* norm, const int32_t* ssao, int size, int32_t* output) {
+    #pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < size; ++y)
+        for (int x = 0; x < size; ++x) {
+            const int h = depth[x + y * size];
+            if (!h) continue;
+            const uint8_t s = (uint8_t)ssao[x + y * size];
+            const fx_v3 normal = fx_unpack_normal(norm[x + y * size]);
+            const fx_v3 pos = fx_mk(fx_ndc((float)x, size), fx_ndc((float)y, size), fx_ndc((float)h, size));
+            const fx_v3 ld = fx_norm(fx_mk(5.0f - pos.x, 5.0f - pos.y, 10.0f - pos.z));
+            float light = fmaxf(0.0f, fx_dot(ld, normal)) * 0.8f;
+            light *= (float)s / 255.0f;
+            light += 0.2f;
+            if (light < 0.0f) light = 0.0f; else if (light > 1.0f) light = 1.0f;
+            const uint32_t color = (uint8_t)fx_f2u(light * 255.0f);
+            output[x + y * size] = (int32_t)((0xFFu << 24) | (color << 16) | (color << 8) | color);
+        }
+}
+
+/* Effects::drawSSAO (effects.cu:253-275) and Effects::drawShaded (effects.cu:277-297). */
+void mpro_fx_ssao(const int32_t* depth, const uint32_t* norm, const float* kernel, const float* rvecs, int size,
+                  int32_t* tmp, int32_t* image) {
+    memset(tmp, 0, sizeof(int32_t) * (size_t)size * size);
+    memset(image, 0, sizeof(int32_t) * (size_t)size * size);
+    mpro_fx_draw_ssao(depth, norm, kernel, rvecs, size, tmp);
+    mpro_fx_blur_ssao(depth, tmp, size, image);
+}
+void mpro_fx_shaded(const int32_t* depth, const uint32_t* norm, const float* kernel, const float* rvecs, int size,
+                    int32_t* tmp, int32_t* image) {
+    memset(tmp, 0, sizeof(int32_t) * (size_t)size * size);
+    memset(image, 0, sizeof(int32_t) * (size_t)size * size);
+    mpro_fx_draw_ssao(depth, norm, kernel, rvecs, size, image);
+    mpro_fx_blur_ssao(depth, image, size, tmp);
+    mpro_fx_draw_shaded(depth, norm, tmp, size, image);
 }

@@ -60,6 +60,28 @@ void ref_render3d(void* c, void* t, const float* mat4_colmajor) {
     static_cast<mpr::Context*>(c)->render3D(*static_cast<mpr::Tape*>(t), m);
 }
 
+void ref_render2d_brute(void* c, void* t, const float* mat3_colmajor, float z) {
+    Eigen::Matrix3f m;
+    memcpy(m.d, mat3_colmajor, sizeof(float) * 9);
+    static_cast<mpr::Context*>(c)->render2D_brute(*static_cast<mpr::Tape*>(t), m, z);
+}
+// The heatmap variants return a managed S*S float array owned by the caller; it is copied out
+// and released here.
+void ref_render2d_heatmap(void* c, void* t, const float* mat3_colmajor, float z, float* heat_out) {
+    Eigen::Matrix3f m;
+    memcpy(m.d, mat3_colmajor, sizeof(float) * 9);
+    mpr::Context* ctx = static_cast<mpr::Context*>(c);
+    auto h = ctx->render2D_heatmap(*static_cast<mpr::Tape*>(t), m, z);
+    memcpy(heat_out, h.get(), sizeof(float) * size_t(ctx->image_size_px) * ctx->image_size_px);
+}
+void ref_render3d_heatmap(void* c, void* t, const float* mat4_colmajor, float* heat_out) {
+    Eigen::Matrix4f m;
+    memcpy(m.d, mat4_colmajor, sizeof(float) * 16);
+    mpr::Context* ctx = static_cast<mpr::Context*>(c);
+    auto h = ctx->render3D_heatmap(*static_cast<mpr::Tape*>(t), m);
+    memcpy(heat_out, h.get(), sizeof(float) * size_t(ctx->image_size_px) * ctx->image_size_px);
+}
+
 int32_t* ref_filled(void* c, int stage) {
     return static_cast<mpr::Context*>(c)->stages[stage].filled.get();
 }

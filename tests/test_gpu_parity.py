@@ -192,3 +192,100 @@ def test_full_size_headline_configs():
     assert h.max() < 1024 and ((h != 0) == (n != 0)).all()     # a normal exactly where there is depth
     assert ((n >> 24) == 0xFF)[n != 0].all()
     ctx.close()
+
+
+@pytest.mark.parametrize("model,size", [("architecture", 256), ("bear", 256), ("gears_3d", 512)])
+def test_effects_match_cpu_restatement(model, size):
+    """mpr::Effects::drawSSAO / drawShaded (reference src/effects.cu:253-297) on a real 3D frame.
+    The effect kernels are built without FMA contraction, like the restatement, so the two can
+    only differ in libdevice powf vs t*t (an ulp inside a sum that is then truncated to 8 bits):
+    tolerance = at most 1 grey level, on at most 0.1 % of the pixels."""
+    ctx, tape = render(model, 3, size)
+    depth, normals = ctx.image().copy(), ctx.normals().copy()
+    assert (depth != 0).sum() > size * size // 20
+    fx = capi.Effects()
+    for shaded in (False, True):
+        (fx.drawShaded if shaded else fx.drawSSAO)(ctx)
+        got = fx.image().copy()
+        want, _ = oracle.effects(depth, normals, fx.kernel, fx.rvecs, shaded=shaded)
+        if shaded:
+            assert ((got >> 24) & 0xff)[depth != 0].min() == 0xff and (got[depth == 0] == 0).all()
+            got, want = got & 0xff, want & 0xff
+        diff = np.abs(got.astype(np.int64) - want.astype(np.int64))
+        assert diff.max() <= 1, (model, shaded, int(diff.max()))
+        assert (diff != 0).mean() <= 1e-3, (model, shaded, float((diff != 0).mean()))
+    fx.close()
+    ctx.close()
+
+
+@pytest.mark.parametrize("model,size", [("hello_world", 256), ("prospero", 512)])
+def test_brute_force_frame(model, size):
+    """Context::render2D_brute (context.cu:1461-1508): same image as the subdivided frame, as the
+    CPU restatement and - when it travelled - the reference build produce it."""
+    cells = load_tape(model)
+    ctx, tape = render(model, 2, size)
+    fancy = ctx.image().copy()
+    ctx.render2D_brute(tape)
+    got = ctx.image().copy()
+    assert np.array_equal(got, fancy)
+    assert ctx.tiles(3)["position"].tolist() == list(range((size // 8) ** 2))
+    o = oracle.CpuOracle(size, SUBTAPES)
+    o.render2D_brute(cells)
+    assert np.array_equal(got, o.image())
+    o.close()
+    if oracle.ref_available():
+        r = oracle.RefGpu(size)
+        r.render2D_brute(cells)
+        assert np.array_equal(got, r.image())
+        r.close()
+    ctx.render2D(tape)                       # the context is still good for ordinary frames
+    assert np.array_equal(ctx.image(), fancy)
+    ctx.close()
+
+
+@pytest.mark.parametrize("model,size", [("hello_world", 256), ("prospero", 1024), ("involute_gear_2d", 512)])
+def test_work_meter_2d_is_exact(model, size):
+    """render2D_heatmap (context.cu:1984-2146).  2D frames have no occlusion races, so the meter
+    is deterministic: integer-exact against the restatement, and equal to the reference build's
+    float atomics up to their summation order."""
+    cells = load_tape(model)
+    ctx, tape = render(model, 2, size)
+    image = ctx.image().copy()
+    heat = ctx.render2D_heatmap(tape)
+    assert np.array_equal(ctx.image(), image)
+    o = oracle.CpuOracle(size, SUBTAPES)
+    want, units = o.render2D_heatmap(cells)
+    assert np.array_equal(heat, want)
+    o.close()
+    if oracle.ref_available():
+        r = oracle.RefGpu(size)
+        ref = r.render2D_heatmap(cells)
+        np.testing.assert_allclose(heat, ref, rtol=2e-5, atol=0)
+        r.close()
+    ctx.close()
+
+
+@pytest.mark.parametrize("model,size", [("hello_world", 128), ("architecture", 256)])
+def test_work_meter_3d(model, size):
+    """render3D_heatmap (context.cu:2148-2340).  In 3D the reference's own meter depends on the
+    order in which tiles land in the depth image (in-kernel occlusion tests decide which tiles
+    push and which voxel columns run), so only the frame itself is exact; the metered work must
+    cover at least the root walk and agree with the other implementations in aggregate."""
+    cells = load_tape(model)
+    ctx, tape = render(model, 3, size)
+    depth, normals = ctx.image().copy(), ctx.normals().copy()
+    heat = ctx.render3D_heatmap(tape)
+    assert np.array_equal(ctx.image(), depth) and np.array_equal(ctx.normals(), normals)
+    n = len(cells) - 2
+    tps = size // 64
+    assert heat.min() >= np.float32(tps / 4096.0) * np.float32(0.999)      # tps level-0 tiles above every pixel
+    o = oracle.CpuOracle(size, SUBTAPES)
+    want, _ = o.render3D_heatmap(cells)
+    assert abs(float(heat.sum()) / float(want.sum()) - 1.0) < 0.25
+    o.close()
+    if oracle.ref_available():
+        r = oracle.RefGpu(size)
+        ref = r.render3D_heatmap(cells)
+        assert abs(float(heat.sum()) / float(ref.sum()) - 1.0) < 0.25
+        r.close()
+    ctx.close()

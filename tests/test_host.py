@@ -110,6 +110,22 @@ def test_packer_folds_constants_and_dedups():
     assert ops == [13, 2]      # ADD_LHS_IMM 6, SQUARE
 
 
+def test_shared_affine_terms_are_collected():
+    # libfive's load-time affine collapse (cache.cpp:463-501): (x + 1) + (x + 2) -> x*2 + 3, and
+    # (2*y - x) - (y - 3*x) -> (y + x*2) - 0: terms with equal coefficients are summed first
+    X, Y, ADD, MUL, SUB = 2, 3, 20, 21, 24
+    nodes = [(X,), ("const", 1.0), ("const", 2.0), (ADD, 0, 1), (ADD, 0, 2), (ADD, 3, 4)]
+    cells = capi.tape_from_frep(_frep(nodes))
+    imm = lambda c: float(np.frombuffer(np.uint32(int(c) >> 32).tobytes(), dtype="<f4")[0])
+    assert [(int(c & 0xFF), imm(c)) for c in cells[1:-1]] == [(15, 2.0), (13, 3.0)]   # MUL_LHS_IMM 2, ADD_LHS_IMM 3
+    nodes = [(X,), (Y,), ("const", 2.0), ("const", 3.0), (MUL, 2, 1), (SUB, 4, 0), (MUL, 3, 0), (SUB, 1, 6), (SUB, 5, 7)]
+    cells = capi.tape_from_frep(_frep(nodes))
+    assert [(int(c & 0xFF), imm(c)) for c in cells[1:-1]] == [(15, 2.0), (14, 0.0)]   # x*2, then y + that
+    # without simplification the expression is packed as written
+    raw = capi.tape_from_frep(_frep(nodes), simplify=False)
+    assert len(raw) - 2 == 5
+
+
 def test_tape_create_validates_before_touching_the_device():
     L = capi.lib()
     h = C.c_void_p()
@@ -128,3 +144,50 @@ def test_ctx_create_rejects_bad_sizes():
     assert L.mprb_ctx_create(100, None, C.byref(h)) == 2
     assert L.mprb_ctx_create(0, None, C.byref(h)) == 2
     assert b"multiple of 64" in L.mprb_last_error()
+
+
+def test_cpu_heightmap_stand_in_renders_the_driver_default_shape(tmp_path):
+    """render_2d.cpp / render_3d.cpp write an out_cpu.png through libfive::Heightmap::render; the
+    stand-in the drivers link (mpr_b200/shim/src/heightmap_render.cpp) must get the two-sphere
+    default shape right: silhouettes, top height, +z normal on the pole, valid PNG files."""
+    import subprocess
+    exe = ROOT / "build" / "drivers" / "heightmap_check"
+    if not exe.exists():
+        pytest.skip("build/drivers/heightmap_check not built (make drivers)")
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    filled3, filled2, wrong, zmax, top = r.stdout.split()
+    assert int(wrong) == 0
+    assert 380 <= int(filled2) <= 430 and int(filled3) == int(filled2)        # 2 discs of radius 8 voxels: ~402
+    assert abs(float(zmax) - 0.234375) < 1e-6                                  # highest voxel centre below z = 0.25
+    n = int(top, 16)
+    assert n >> 24 == 0xff and (n >> 16) & 0xff >= 0xf8 and abs((n & 0xff) - 0x80) <= 8
+    for name, kind in (("depth.png", 0), ("norm.png", 6)):
+        png = (tmp_path / name).read_bytes()
+        assert png[:8] == b"\x89PNG\r\n\x1a\n"
+        w, h, depth, colour = __import__("struct").unpack(">IIBB", png[16:26])
+        assert (w, h) == (64, 64) and colour == kind and depth == (16 if kind == 0 else 8)
+
+
+def test_dump_tape_reproduces_the_kernel_libfive_generated_for_brute_cu():
+    """benchmark/brute.cu:44-58 holds the body that the reference's dump_tape (built on the real
+    libfive) printed for the default two-sphere shape.  The same driver built on this repository's
+    Tree stand-in must print the same statements in the same order - a known answer for operator
+    overloads, hash-consing, commutative rebalancing and orderedDfs together."""
+    import subprocess
+    exe = ROOT / "build" / "drivers" / "dump_tape"
+    if not exe.exists():
+        pytest.skip("build/drivers/dump_tape not built (needs the reference sources at build time)")
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60).stdout
+    names = {}
+    body = []
+    for line in out.splitlines():
+        m = re.match(r"\s*const float (v\d+) = (.*);", line)
+        if not m:
+            continue
+        names[m.group(1)] = f"v{len(names)}"
+        body.append(re.sub(r"v\d+", lambda k: names[k.group(0)], m.group(2)))
+    assert body == [
+        "x + 0.500000f", "v0 * v0", "y * y", "z * z", "v2 + v3", "v1 + v4", "sqrt(v5)", "v6 - 0.250000f",
+        "x - 0.500000f", "v8 * v8", "v9 + v4", "sqrt(v10)", "v11 - 0.250000f", "min(v7, v12)"]
+    assert "if (v13 < 0.0f)" in re.sub(r"v\d+", lambda k: names.get(k.group(0), k.group(0)), out)

@@ -192,3 +192,109 @@ def test_tape_evaluates_the_expression_it_was_built_from():
     r = np.sqrt(pts[:, 0] * pts[:, 0] + pts[:, 1] * pts[:, 1])
     want = np.maximum(r - np.float32(1.0), np.float32(0.5) - r)
     assert np.array_equal(out, want.astype(np.float32))
+
+
+# ---- post-effects restatement (reference src/effects.cu); parity unpinned, so these pin properties ----
+
+def _plane(size, h, nz_only=True):
+    depth = np.full((size, size), h, dtype=np.int32)
+    normals = np.full((size, size), 128 | (128 << 8) | (255 << 16) | (0xff << 24), dtype=np.uint32)
+    return depth, normals
+
+
+def test_effect_samples_follow_the_reference_constructor():
+    from mpr_b200.capi import glibc_effect_samples
+    kernel, rvecs = glibc_effect_samples()
+    assert kernel.shape == (64, 3) and rvecs.shape == (256, 3)
+    i = np.arange(64, dtype=np.float32) / np.float32(63)
+    np.testing.assert_allclose(np.linalg.norm(kernel, axis=1), i * i * 0.9 + 0.1, rtol=1e-5)   # effects.cu:236-238
+    assert (kernel[:, 2] >= 0).all()                                                         # hemisphere
+    np.testing.assert_allclose(np.linalg.norm(rvecs, axis=1), 1.0, rtol=1e-5)
+    assert (rvecs[:, 2] == 0).all()
+    k2, r2 = glibc_effect_samples()
+    assert (k2 == kernel).all() and (r2 == rvecs).all()
+
+
+def test_ssao_of_an_unoccluded_plane_is_white_and_of_nothing_is_black():
+    from mpr_b200.capi import glibc_effect_samples
+    kernel, rvecs = glibc_effect_samples()
+    size = 64
+    depth, normals = _plane(size, 20)
+    image, tmp = oracle.effects(depth, normals, kernel, rvecs)
+    # every sample lies above a plane facing +z (kernel z > 0): no occlusion, away from the frame edge
+    assert (tmp[8:-8, 8:-8] == 255).all() and (image[8:-8, 8:-8] == 255).all()
+    image, tmp = oracle.effects(np.zeros_like(depth), normals, kernel, rvecs)
+    assert not tmp.any() and not image.any()
+
+
+def test_ssao_darkens_the_foot_of_a_step():
+    from mpr_b200.capi import glibc_effect_samples
+    kernel, rvecs = glibc_effect_samples()
+    size = 128
+    depth, normals = _plane(size, 20)
+    depth[:, 64:] = 30                      # a wall 10 voxels high (0.16 in NDC, RADIUS = 0.1) right of x = 64
+    image, tmp = oracle.effects(depth, normals, kernel, rvecs)
+    near, far = tmp[32:96, 60:64].mean(), tmp[32:96, 20:40].mean()
+    assert far == 255 and near < 240
+    assert image[32:96, 61].mean() < 250    # the blur keeps the darkening
+
+
+def test_shading_of_a_plane_matches_the_closed_form():
+    from mpr_b200.capi import glibc_effect_samples
+    kernel, rvecs = glibc_effect_samples()
+    size = 64
+    depth, normals = _plane(size, 20)
+    image, _ = oracle.effects(depth, normals, kernel, rvecs, shaded=True)
+    assert ((image >> 24) & 0xff == 0xff).all()
+    grey = image & 0xff
+    assert ((image >> 8) & 0xff == grey).all() and ((image >> 16) & 0xff == grey).all()
+    xs = 2.0 * ((np.arange(size) + 0.5) / size - 0.5)
+    px, py = np.meshgrid(xs, xs)
+    pz = 2.0 * ((20 + 0.5) / size - 0.5)
+    l = np.stack([5 - px, 5 - py, 10 - pz + 0 * px])
+    want = np.clip(l[2] / np.linalg.norm(l, axis=0) * (127 / 127.0) * 0.8 + 0.2, 0, 1) * 255     # effects.cu:199-217
+    inner = (slice(8, -8), slice(8, -8))
+    assert np.abs(grey[inner] - np.floor(want[inner])).max() <= 1
+
+
+# ---- analysis variants: brute force and the work meter (reference context.cu:1461-2340) ----
+
+@pytest.mark.parametrize("model,size", [("hello_world", 128), ("prospero", 256)])
+def test_brute_force_frame_equals_the_subdivided_one(model, size):
+    cells = load_tape(model)
+    o = oracle.CpuOracle(size, 100000)
+    o.render2D(cells)
+    fancy = o.image().copy()
+    o.render2D_brute(cells)
+    assert np.array_equal(o.image(), fancy)
+    assert o._tile_count(3) == (size // 8) ** 2
+    o.close()
+
+
+def test_work_meter_charges_every_pixel_for_every_level_that_covers_it():
+    cells = load_tape("prospero")
+    n = len(cells) - 2
+    size = 1024
+    o = oracle.CpuOracle(size, 100000)
+    o.render2D(cells)
+    image = o.image().copy()
+    heat, units = o.render2D_heatmap(cells)
+    assert np.array_equal(o.image(), image)                 # metering does not change the frame
+    # a tile spreads cells / px^2 over px^2 pixels, so the total is a whole number of cells
+    assert int(units.sum()) % 4096 == 0
+    # every pixel is covered by one level-0 tile, whose forward walk visits the whole tape:
+    # n cells over 64 x 64 pixels
+    assert units.min() >= n and heat.min() >= np.float32(1.0 / 4096) * np.float32(0.999)
+    assert np.allclose(heat, units / 4096.0 / n, rtol=1e-6)
+    # a level-0 tile that is proven empty or filled costs exactly one walk of the root tape
+    t0 = o.tiles(0)
+    dead = t0["position"] == -1
+    assert dead.any()
+    k = int(np.flatnonzero(dead)[0])
+    ty, tx = divmod(k, size // 64)
+    assert (units[ty * 64:(ty + 1) * 64, tx * 64:(tx + 1) * 64] == n).all()
+    # ambiguous tiles were walked forwards and backwards, then their children were charged too
+    k = int(np.flatnonzero(~dead)[0])
+    ty, tx = divmod(k, size // 64)
+    assert (units[ty * 64:(ty + 1) * 64, tx * 64:(tx + 1) * 64] >= 2 * n).all()
+    o.close()
