@@ -15,7 +15,7 @@ all: mpr_b200/libmprb.so drivers
 mpr_b200/libmprb.so: $(OBJS)
 	$(NVCC) -shared $(ARCH) -Xlinker -Bsymbolic -o $@ $(OBJS)
 
-$(BUILD)/%.o: %.cu $(wildcard mpr_b200/csrc/*.cuh) include/mprb.h
+$(BUILD)/%.o: %.cu $(wildcard mpr_b200/csrc/*.cuh) $(wildcard mpr_b200/csrc/*.inc) include/mprb.h
 	@mkdir -p $(dir $@)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

@@ -919,62 +919,160 @@ k_upsample_filled(const int32_t* __restrict__ prev, int32_t* __restrict__ image,
 // Clause semantics: context.cu:887-920.  There is no a*b+c shape in any clause,
 // so nothing here can be contracted; the _rn intrinsics just make that explicit.
 // `slots` is this lane's shared-space base address (slot s at slots + s * 256).
+// The clause loop of the float pass, written in PTX (generated: tools/gen_float_loop.py ->
+// float_loop_ptx.inc).
+//
+// The C++ form of this loop compiles to ~40 SASS instructions per clause - a compare/branch
+// tree for the 30-way switch, divergence bookkeeping (BSSY/BSYNC) around it, shift+mask+add
+// per operand address - and moves 7 shared-memory wavefronts per clause (clause word, two
+// operand rows, one result row), which made the float pass first issue-bound (84 % issue-active,
+// profiles/r01_ncu_k_eval_voxels.csv) and then, with a plain PTX loop, shared-memory bound (86 %
+// of the LSU data pipe).  This version attacks both:
+//   * dispatch is one indexed branch through a table (`brx.idx.uni`; every lane of the warp runs
+//     the same tape, hence `.uni` and no reconvergence stack), and every handler jumps straight
+//     back to the head of the loop;
+//   * the tape packer reuses slots LIFO, so most clauses consume the previous clause's result
+//     and overwrite its slot (bear: 60 % / 66 %).  annotate_chunk() marks those cases in the three
+//     spare bits of the opcode byte when a chunk arrives, and the table has a handler per
+//     (opcode, hints) that takes the operand from the result registers and skips the dead store;
+//     operands a clause does not use are never loaded.
+// Runs clauses starting at the cell AFTER `cp` until it meets one it does not handle - END, JUMP,
+// or a libdevice transcendental (SIN..LOG) - and returns with cp on that cell and its two words
+// in w / imm.  `sb` is this lane's slot base in shared space (slot s at sb + 256 s).
+__device__ __forceinline__ void run_float_clauses(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
+{
+    asm volatile(
+#include "float_loop_ptx.inc"
+        : "+r"(cp), "=&r"(w), "=&r"(imm)
+        : "r"(sb)
+        : "memory");
+}
+
+// Opcode classes for the hints (bit i = opcode i).  FAST: handled inside the PTX loop.
+constexpr uint32_t kFastOps = 0x3fffe81cu;      // everything but END, JUMP, SIN..EXP, LOG
+constexpr uint32_t kUsesLhs = (1u << OP_SQUARE) | (1u << OP_SQRT) | (1u << OP_NEG) | (1u << OP_ABS) | (1u << OP_ADD_LI) |
+                              (1u << OP_ADD_LR) | (1u << OP_MUL_LI) | (1u << OP_MUL_LR) | (1u << OP_MIN_LI) |
+                              (1u << OP_MIN_LR) | (1u << OP_MAX_LI) | (1u << OP_MAX_LR) | (1u << OP_SUB_LI) |
+                              (1u << OP_SUB_LR) | (1u << OP_DIV_LI) | (1u << OP_DIV_LR) | (1u << OP_COPY_LHS);
+constexpr uint32_t kUsesRhs = (1u << OP_ADD_LR) | (1u << OP_MUL_LR) | (1u << OP_MIN_LR) | (1u << OP_MAX_LR) |
+                              (1u << OP_SUB_IR) | (1u << OP_SUB_LR) | (1u << OP_DIV_IR) | (1u << OP_DIV_LR) |
+                              (1u << OP_COPY_RHS);
+static_assert(kFastOps == (((1u << 30) - 1) & ~((1u << OP_END) | (1u << OP_JUMP) | (1u << OP_SIN) | (1u << OP_COS) |
+                                               (1u << OP_ASIN) | (1u << OP_ACOS) | (1u << OP_ATAN) | (1u << OP_EXP) |
+                                               (1u << OP_LOG))), "kFastOps");
+
+// Writes the forwarding hints (see tools/gen_float_loop.py) into the opcode bytes of a freshly
+// arrived raw chunk.  A hint only ever relates a cell to its neighbour in memory, and the loop
+// only ever runs a cell right after that neighbour (entries land after an END / JUMP / slow
+// cell, which never forward), so stale cells elsewhere in the chunk do not matter.
+__device__ __forceinline__ void annotate_chunk(uint32_t buf)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t byte0[2];
+    #pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int j = lane + 32 * k;
+        const uint32_t w = lds_u32(buf + j * 8);
+        const uint32_t wp = j > 0 ? lds_u32(buf + (j - 1) * 8) : 0u;
+        const uint32_t wn = j < kChunk - 1 ? lds_u32(buf + (j + 1) * 8) : 0u;
+        auto fast = [](uint32_t x) { return (x & 0xe0u) == 0 && ((kFastOps >> (x & 31u)) & 1u); };
+        const uint32_t op = w & 31u;
+        const uint32_t prev_out = (wp >> 8) & 0xff;
+        uint32_t flags = 0;
+        if (fast(w)) {
+            if (fast(wp)) {
+                if (((kUsesLhs >> op) & 1u) && ((w >> 16) & 0xff) == prev_out) flags |= 0x20;
+                if (((kUsesRhs >> op) & 1u) && (w >> 24) == prev_out) flags |= 0x40;
+            }
+            if (fast(wn) && ((wn >> 8) & 0xff) == ((w >> 8) & 0xff)) flags |= 0x80;
+        }
+        byte0[k] = (w & 0xff) | flags;
+    }
+    __syncwarp();
+    sts_u8(buf + lane * 8, byte0[0]);
+    sts_u8(buf + (lane + 32) * 8, byte0[1]);
+    __syncwarp();
+}
+
+// One clause in C++ (context.cu:887-920): the slot-renaming variant runs every clause through
+// this, the PTX loop above only the transcendental ones.
+__device__ __forceinline__ float2 float_clause(uint32_t op, float2 L, float2 R, float imm)
+{
+    switch (op) {
+        case OP_SQUARE: return make_float2(__fmul_rn(L.x, L.x), __fmul_rn(L.y, L.y));
+        case OP_SQRT:   return make_float2(sqrtf(L.x), sqrtf(L.y));
+        case OP_NEG:    return make_float2(-L.x, -L.y);
+        case OP_SIN:    return make_float2(sinf(L.x), sinf(L.y));
+        case OP_COS:    return make_float2(cosf(L.x), cosf(L.y));
+        case OP_ASIN:   return make_float2(asinf(L.x), asinf(L.y));
+        case OP_ACOS:   return make_float2(acosf(L.x), acosf(L.y));
+        case OP_ATAN:   return make_float2(atanf(L.x), atanf(L.y));
+        case OP_EXP:    return make_float2(expf(L.x), expf(L.y));
+        case OP_ABS:    return make_float2(fabsf(L.x), fabsf(L.y));
+        case OP_LOG:    return make_float2(logf(L.x), logf(L.y));
+        case OP_ADD_LI: return make_float2(__fadd_rn(L.x, imm), __fadd_rn(L.y, imm));
+        case OP_ADD_LR: return make_float2(__fadd_rn(L.x, R.x), __fadd_rn(L.y, R.y));
+        case OP_MUL_LI: return make_float2(__fmul_rn(L.x, imm), __fmul_rn(L.y, imm));
+        case OP_MUL_LR: return make_float2(__fmul_rn(L.x, R.x), __fmul_rn(L.y, R.y));
+        case OP_MIN_LI: return make_float2(fminf(L.x, imm), fminf(L.y, imm));
+        case OP_MIN_LR: return make_float2(fminf(L.x, R.x), fminf(L.y, R.y));
+        case OP_MAX_LI: return make_float2(fmaxf(L.x, imm), fmaxf(L.y, imm));
+        case OP_MAX_LR: return make_float2(fmaxf(L.x, R.x), fmaxf(L.y, R.y));
+        case OP_SUB_LI: return make_float2(__fsub_rn(L.x, imm), __fsub_rn(L.y, imm));
+        case OP_SUB_IR: return make_float2(__fsub_rn(imm, R.x), __fsub_rn(imm, R.y));
+        case OP_SUB_LR: return make_float2(__fsub_rn(L.x, R.x), __fsub_rn(L.y, R.y));
+        case OP_DIV_LI: return make_float2(__fdiv_rn(L.x, imm), __fdiv_rn(L.y, imm));
+        case OP_DIV_IR: return make_float2(__fdiv_rn(imm, R.x), __fdiv_rn(imm, R.y));
+        case OP_DIV_LR: return make_float2(__fdiv_rn(L.x, R.x), __fdiv_rn(L.y, R.y));
+        case OP_COPY_IMM: return make_float2(imm, imm);
+        case OP_COPY_LHS: return L;
+        case OP_COPY_RHS: return R;
+        default: return L;
+    }
+}
+__device__ __forceinline__ float2 float_clause_libdevice(uint32_t op, float2 L)
+{
+    switch (op) {
+        case OP_SIN:  return make_float2(sinf(L.x), sinf(L.y));
+        case OP_COS:  return make_float2(cosf(L.x), cosf(L.y));
+        case OP_ASIN: return make_float2(asinf(L.x), asinf(L.y));
+        case OP_ACOS: return make_float2(acosf(L.x), acosf(L.y));
+        case OP_ATAN: return make_float2(atanf(L.x), atanf(L.y));
+        case OP_EXP:  return make_float2(expf(L.x), expf(L.y));
+        default:      return make_float2(logf(L.x), logf(L.y));
+    }
+}
+
 template <bool REMAP>
 __device__ __forceinline__ float2 walk_float(TapeStream<REMAP>& ts, int tape, Slots2<REMAP>& slots, unsigned& cells)
 {
-    ts.fetch(tape);
+    if (ts.fetch(tape) && !REMAP) annotate_chunk(ts.buf);
     uint32_t cp = ts.rd + ((tape & (kChunk - 1)) << 3);
     uint32_t seg = cp;
-    uint32_t w;
+    uint32_t w, immb;
     for (;;) {
-        cp += 8;
-        const uint2 d = lds_u2(cp);
-        w = d.x;
+        if (REMAP) {
+            cp += 8;
+            const uint2 d = lds_u2(cp);
+            w = d.x;
+            immb = d.y;
+        } else {
+            run_float_clauses(cp, w, immb, slots.base);
+        }
         const uint32_t op = w & 0xff;
         if (op <= OP_JUMP) {
             cells += (cp - seg) >> 3;
             if (op == OP_END) { --cells; break; }
-            const int t = ts.base + int((cp - ts.rd) >> 3) + int32_t(d.y);
-            ts.fetch(t);
+            const int t = ts.base + int((cp - ts.rd) >> 3) + int32_t(immb);
+            if (ts.fetch(t) && !REMAP) annotate_chunk(ts.buf);
             cp = ts.rd + ((t & (kChunk - 1)) << 3);
             seg = cp;
             continue;
         }
-        const float imm = __uint_as_float(d.y);
         const float2 L = slots.ld(off_lhs2(w));
-        const float2 R = slots.ld(off_rhs2(w));
         float2 o;
-        switch (op) {
-            case OP_SQUARE: o = make_float2(__fmul_rn(L.x, L.x), __fmul_rn(L.y, L.y)); break;
-            case OP_SQRT:   o = make_float2(sqrtf(L.x), sqrtf(L.y)); break;
-            case OP_NEG:    o = make_float2(-L.x, -L.y); break;
-            case OP_SIN:    o = make_float2(sinf(L.x), sinf(L.y)); break;
-            case OP_COS:    o = make_float2(cosf(L.x), cosf(L.y)); break;
-            case OP_ASIN:   o = make_float2(asinf(L.x), asinf(L.y)); break;
-            case OP_ACOS:   o = make_float2(acosf(L.x), acosf(L.y)); break;
-            case OP_ATAN:   o = make_float2(atanf(L.x), atanf(L.y)); break;
-            case OP_EXP:    o = make_float2(expf(L.x), expf(L.y)); break;
-            case OP_ABS:    o = make_float2(fabsf(L.x), fabsf(L.y)); break;
-            case OP_LOG:    o = make_float2(logf(L.x), logf(L.y)); break;
-            case OP_ADD_LI: o = make_float2(__fadd_rn(L.x, imm), __fadd_rn(L.y, imm)); break;
-            case OP_ADD_LR: o = make_float2(__fadd_rn(L.x, R.x), __fadd_rn(L.y, R.y)); break;
-            case OP_MUL_LI: o = make_float2(__fmul_rn(L.x, imm), __fmul_rn(L.y, imm)); break;
-            case OP_MUL_LR: o = make_float2(__fmul_rn(L.x, R.x), __fmul_rn(L.y, R.y)); break;
-            case OP_MIN_LI: o = make_float2(fminf(L.x, imm), fminf(L.y, imm)); break;
-            case OP_MIN_LR: o = make_float2(fminf(L.x, R.x), fminf(L.y, R.y)); break;
-            case OP_MAX_LI: o = make_float2(fmaxf(L.x, imm), fmaxf(L.y, imm)); break;
-            case OP_MAX_LR: o = make_float2(fmaxf(L.x, R.x), fmaxf(L.y, R.y)); break;
-            case OP_SUB_LI: o = make_float2(__fsub_rn(L.x, imm), __fsub_rn(L.y, imm)); break;
-            case OP_SUB_IR: o = make_float2(__fsub_rn(imm, R.x), __fsub_rn(imm, R.y)); break;
-            case OP_SUB_LR: o = make_float2(__fsub_rn(L.x, R.x), __fsub_rn(L.y, R.y)); break;
-            case OP_DIV_LI: o = make_float2(__fdiv_rn(L.x, imm), __fdiv_rn(L.y, imm)); break;
-            case OP_DIV_IR: o = make_float2(__fdiv_rn(imm, R.x), __fdiv_rn(imm, R.y)); break;
-            case OP_DIV_LR: o = make_float2(__fdiv_rn(L.x, R.x), __fdiv_rn(L.y, R.y)); break;
-            case OP_COPY_IMM: o = make_float2(imm, imm); break;
-            case OP_COPY_LHS: o = L; break;
-            case OP_COPY_RHS: o = R; break;
-            default: o = L; break;
-        }
+        if (REMAP) o = float_clause(op, L, slots.ld(off_rhs2(w)), __uint_as_float(immb));
+        else o = float_clause_libdevice(op, L);
         slots.st(off_out2(w), o);
     }
     return slots.ld(off_out2(w));

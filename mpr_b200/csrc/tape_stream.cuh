@@ -56,6 +56,11 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
 __device__ __forceinline__ void sts_u2(uint32_t addr, uint2 v) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -210,11 +215,13 @@ struct TapeStream {
 
     // Forward walking: makes the chunk of arena cell `index` resident; the walk continues at
     // index + 1, so cells up to `index` in that chunk are not part of this tape.
-    __device__ __forceinline__ void fetch(int index) {
+    // Returns true when a new chunk was brought in (false: it was already resident).
+    __device__ __forceinline__ bool fetch(int index) {
         const int want = index & ~(kChunk - 1);
-        if (want == base) return;
+        if (want == base) return false;
         load_chunk(want);
         if (REMAP) rename((index & (kChunk - 1)) + 1, true);
+        return true;
     }
 
     // Backward walking (tape push): every id was seen on the way forward, so the whole chunk
