@@ -284,9 +284,11 @@ def run_mine(args, workloads):
 
         def roof(k):
             ach = bytes_by_kernel[k] / (per_kernel[k] * 1e-3) / 1e9 if per_kernel[k] > 0 else 0.0
-            return {"kernel": "k_" + k, "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 5), "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_step": int(bytes_by_kernel[k]), "kernel_ms_per_step": round(per_kernel[k], 4)}
+            out = {"kernel": "k_" + k, "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
+                   "frac": round(ach / peak, 5), "traffic": None, "peak_source": peak_src,
+                   "algorithmic_bytes_per_step": int(bytes_by_kernel[k]), "kernel_ms_per_step": round(per_kernel[k], 4)}
+            out.update(ncu_capture("k_" + k))
+            return out
 
         h2d = sum(j["cells"].nbytes + (64 if j["dim"] == 3 else 36) for j in jobs)
         d2h = sum(j["size"] ** 2 * 4 * (2 if j["dim"] == 3 else 1) for j in jobs)
@@ -378,6 +380,37 @@ def run_reference(args, workloads):
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(workloads)
     print(json.dumps(line), flush=True)
+
+
+def ncu_capture(kernel: str) -> dict:
+    """DRAM traffic per launch (+ what actually bounds the kernel) from the committed
+    `ncu --set full` capture of this kernel, profiles/*_ncu_<kernel>*.csv (raw page export)."""
+    import csv
+    files = sorted((ROOT / "profiles").glob(f"*_ncu_{kernel}*.csv"))
+    if not files:
+        return {}
+    # one "metric,unit,value" line per metric
+    val, unit = {}, {}
+    for row in csv.reader(files[-1].open()):
+        if len(row) >= 3:
+            val[row[0]], unit[row[0]] = row[2], row[1]
+
+    def num(name, scale=None):
+        try:
+            v = float(val[name])
+        except (KeyError, ValueError):
+            return None
+        if scale is not None:
+            v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit.get(name, "byte"), 1.0)
+        return v
+
+    rd, wr = num("dram__bytes_read.sum", 1), num("dram__bytes_write.sum", 1)
+    return {"traffic": int(rd + wr) if rd is not None and wr is not None else None,
+            "traffic_source": f"profiles/{files[-1].name} (one launch, bear 1024^3 frame)",
+            "ncu": {"issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "lsu_shared_pipe_pct": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                    "warp_instructions": num("smsp__inst_executed.sum"),
+                    "duration_ms_under_ncu": num("gpu__time_duration.sum")}}
 
 
 def main():
