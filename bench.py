@@ -159,7 +159,8 @@ def run_mine(args, workloads):
 
     jobs = []
     for model, dim, size in workloads:
-        ctx = capi.Context(size, device=local, num_subtapes=SUBTAPES, **sharding.cyclic_rows(size, world, rank))
+        shard = sharding.diagonal_tiles if SHARD == "diag" else sharding.cyclic_rows
+        ctx = capi.Context(size, device=local, num_subtapes=SUBTAPES, **shard(size, world, rank))
         cells_pinned = torch.from_numpy(load_tape(model).view(np.int64).copy()).pin_memory()
         cells = cells_pinned.numpy().view(np.uint64)
         tape = capi.Tape(cells)
@@ -173,6 +174,8 @@ def run_mine(args, workloads):
             if dim == 3:
                 ptr, nbytes = ctx.device_normals()
                 job["dev_nrm"] = torch.as_tensor(DevArray(ptr, size * size, "<i4"), device=f"cuda:{local}").view(size, size)
+            if SHARD == "diag":
+                job["exchange"] = sharding.TileExchange(size, world, f"cuda:{local}", n_images=2 if dim == 3 else 1)
         jobs.append(job)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
@@ -183,10 +186,15 @@ def run_mine(args, workloads):
             return 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        # interleaved tile rows -> one all-gather per image; every rank ends up holding the full frame
-        job["dev_img"].copy_(sharding.all_gather_cyclic(job["dev_img"], job["size"]))
-        if job["dim"] == 3:
-            job["dev_nrm"].copy_(sharding.all_gather_cyclic(job["dev_nrm"], job["size"]))
+        if SHARD == "diag":
+            # tile-cyclic: depth and normals blocks travel in ONE all-gather; every rank ends up with the full frame
+            imgs = [job["dev_img"]] + ([job["dev_nrm"]] if job["dim"] == 3 else [])
+            job["exchange"].gather(imgs, imgs)
+        else:
+            # interleaved tile rows -> one all-gather per image
+            job["dev_img"].copy_(sharding.all_gather_cyclic(job["dev_img"], job["size"]))
+            if job["dim"] == 3:
+                job["dev_nrm"].copy_(sharding.all_gather_cyclic(job["dev_nrm"], job["size"]))
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
@@ -195,7 +203,10 @@ def run_mine(args, workloads):
         ctx = job["ctx"]
         (ctx.render2D if job["dim"] == 2 else ctx.render3D)(job["tape"])
         ms = ctx.stats().gpu_ms
-        return ms + gather(job)
+        g = gather(job)
+        job["gather_ms"] = job.get("gather_ms", 0.0) + g
+        job["gather_n"] = job.get("gather_n", 0) + 1
+        return ms + g
 
     def frame_e2e(job):
         ctx = job["ctx"]
@@ -299,11 +310,13 @@ def run_mine(args, workloads):
             "vs_baseline": None, "dtype": "f32", "data": "the reference's benchmark models as packed tapes (tests/golden/tapes)",
             "config": {"workload": "+".join(f"{j['model']}_{j['dim']}d_{j['size']}" for j in jobs),
                        "frames_per_step": n_frames, "view": "2D identity, 3D T(3,2)=0.3 (reference table drivers)",
-                       "parallelism": f"interleaved 64-px tile rows x{world}" + (", 1 NCCL all-gather per image" if world > 1 else ""),
+                       "parallelism": (f"tile-cyclic 64x64-px screen columns x{world}, 1 NCCL all-gather per frame" if SHARD == "diag"
+                                       else f"interleaved 64-px tile rows x{world}, 1 NCCL all-gather per image") if world > 1 else "1 GPU",
                        "num_subtapes": SUBTAPES, "l2": "flushed between steps (256 MiB memset, untimed)",
                        "timing": "CUDA events on the render stream per frame (+ all-gather events), max over ranks",
                        "ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(dev[:, i].mean()) for i, j in enumerate(jobs)},
                        "e2e_ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(e2e[:, i].mean()) for i, j in enumerate(jobs)},
+                       "exchange_ms_per_frame_rank0": {f"{j['model']}_{j['dim']}d_{j['size']}": round(j.get("gather_ms", 0.0) / max(j.get("gather_n", 1), 1), 4) for j in jobs},
                        "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
                        "frame_stats": stats_one},
             "clocks": clk,
@@ -380,6 +393,9 @@ def run_reference(args, workloads):
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(workloads)
     print(json.dumps(line), flush=True)
+
+
+SHARD = os.environ.get("MPRB_SHARD", "diag")      # multi-GPU split: "diag" (tile-cyclic) or "rows" (interleaved rows)
 
 
 def ncu_capture(kernel: str) -> dict:

@@ -67,6 +67,10 @@ typedef struct mprb_ctx_opts {
      * Interleaving tile rows across GPUs balances load far better than contiguous bands. */
     int32_t row_mod;
     int32_t row_rem;
+    /* Tile-cyclic variant: with col_step = 1 a level-0 tile (x, y) belongs to this context iff
+     * (y + x) % row_mod == row_rem - diagonal stripes of 64x64-px screen columns, the finest
+     * independent unit (a 3D column keeps all its z tiles).  0 = whole rows, as above. */
+    int32_t col_step;
 } mprb_ctx_opts;
 
 /* Per-frame counters, filled by the render calls (device-side; no extra syncs). */

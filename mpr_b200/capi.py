@@ -44,6 +44,7 @@ class CtxOpts(C.Structure):
         ("row_end", C.c_int32),
         ("row_mod", C.c_int32),
         ("row_rem", C.c_int32),
+        ("col_step", C.c_int32),
     ]
 
 
@@ -256,10 +257,10 @@ class Context:
     """Mirror of mpr::Context (reference inc/context.hpp:38-73)."""
 
     def __init__(self, image_size_px: int, device: int = -1, num_subtapes: int = 0,
-                 row_begin: int = 0, row_end: int = 0, row_mod: int = 0, row_rem: int = 0):
+                 row_begin: int = 0, row_end: int = 0, row_mod: int = 0, row_rem: int = 0, col_step: int = 0):
         self.image_size_px = image_size_px
         self._h = C.c_void_p()
-        opts = CtxOpts(device, num_subtapes, row_begin, row_end, row_mod, row_rem)
+        opts = CtxOpts(device, num_subtapes, row_begin, row_end, row_mod, row_rem, col_step)
         _check(lib().mprb_ctx_create(image_size_px, C.byref(opts), C.byref(self._h)))
 
     def close(self):

@@ -91,7 +91,7 @@ struct mprb_ctx {
     int device = 0;
     int size = 0;
     int sm_count = 0;
-    int row_begin = 0, row_end = 0, row_mod = 1, row_rem = 0;
+    int row_begin = 0, row_end = 0, row_mod = 1, row_rem = 0, col_step = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     cudaEvent_t ev_k[kMaxLaunches + 1] = {};
@@ -115,6 +115,8 @@ struct mprb_ctx {
     uint64_t* stage_cells = nullptr; // pinned staging for host tapes
     int32_t stage_cells_cap = 0;
     bool serial_root = false;        // debugging / A-B switch: MPRB_SERIAL_ROOT=1
+    int32_t* owned_tiles = nullptr;  // device: level-0 screen tiles (y * tiles_per_side + x) this context renders
+    int n_owned = 0;
     unsigned long long* heat_units = nullptr;   // work meter of render*_heatmap (device, S*S), lazily allocated
     // Host-buffer entry points: the per-tape root plan is cached across frames as long as
     // the caller keeps passing the same cells (the cells themselves are re-uploaded every frame).
@@ -318,6 +320,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         if (c->stage_cells_cap < n_chunked) {
             if (c->stage_cells) cudaFreeHost(c->stage_cells);
     if (c->heat_units) cudaFree(c->heat_units);
+    if (c->owned_tiles) cudaFree(c->owned_tiles);
             c->stage_cells = nullptr;
             MPRB_CUDA(cudaMallocHost(&c->stage_cells, sizeof(uint64_t) * size_t(n_chunked)));
             c->stage_cells_cap = n_chunked;
@@ -375,6 +378,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         ea.row_end = c->row_end;
         ea.row_mod = c->row_mod;
         ea.row_rem = c->row_rem;
+        ea.col_step = c->col_step;
         ea.ctl = c->ctl;
         ea.queue = &c->ctl->queue[q++];
         ea.level = l;
@@ -397,6 +401,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
             ra.row_end = c->row_end;
             ra.row_mod = c->row_mod;
             ra.row_rem = c->row_rem;
+            ra.col_step = c->col_step;
             ra.ctl = c->ctl;
             ra.cells = plan->cells;
             ra.sched = plan->sched;
@@ -471,10 +476,8 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         na.image = c->filled[3];
         na.normals = c->normals;
         na.size = S;
-        na.y_begin = c->row_begin * 64;
-        na.y_end = c->row_end * 64;
-        na.row_mod = c->row_mod;
-        na.row_rem = c->row_rem;
+        na.owned = c->owned_tiles;
+        na.n_owned = c->n_owned;
         na.tiles0 = c->tiles[0];
         na.tiles1 = c->tiles[1];
         na.tiles2 = c->tiles[2];
@@ -576,6 +579,7 @@ int mprb_ctx_create(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx**
     c->row_end = (opts && opts->row_end > 0) ? opts->row_end : tps0;
     c->row_mod = (opts && opts->row_mod > 1) ? opts->row_mod : 1;
     c->row_rem = (opts && opts->row_mod > 1) ? opts->row_rem : 0;
+    c->col_step = (opts && opts->row_mod > 1 && opts->col_step) ? 1 : 0;
     if (c->row_rem < 0 || c->row_rem >= c->row_mod) {
         delete c;
         return fail(MPRB_E_ARG, "row_rem must lie in [0, row_mod)");
@@ -610,6 +614,18 @@ int mprb_ctx_create(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx**
     }
     if ((e = managed_alloc(&c->normals, size_t(image_size_px) * image_size_px, device)) != cudaSuccess)
         return bail(e, "normals");
+    {   // The screen tiles this context owns, for the per-pixel normal pass
+        std::vector<int32_t> owned;
+        for (int ty = c->row_begin; ty < c->row_end; ++ty)
+            for (int tx = 0; tx < tps0; ++tx)
+                if ((ty + c->col_step * tx) % c->row_mod == c->row_rem) owned.push_back(ty * tps0 + tx);
+        c->n_owned = int(owned.size());
+        if ((e = cudaMalloc(&c->owned_tiles, sizeof(int32_t) * std::max<size_t>(owned.size(), 1))) != cudaSuccess)
+            return bail(e, "owned tile list");
+        if ((e = cudaMemcpy(c->owned_tiles, owned.data(), sizeof(int32_t) * owned.size(), cudaMemcpyHostToDevice)) !=
+            cudaSuccess)
+            return bail(e, "owned tile list");
+    }
     const long long chunks = (opts && opts->num_subtapes > 0) ? opts->num_subtapes : 640000;
     c->arena_cells = chunks * kChunk;
     if (c->arena_cells > INT32_MAX) {

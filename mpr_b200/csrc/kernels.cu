@@ -206,7 +206,7 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
             sx = tt % tps;
             sy = (tt / tps) % tps;
             if (DIM == 3) sz = (tt / tps) / tps;
-            inband = (sy >= a.row_begin) && (sy < a.row_end) && (sy % a.row_mod == a.row_rem);
+            inband = (sy >= a.row_begin) && (sy < a.row_end) && ((sy + a.col_step * sx) % a.row_mod == a.row_rem);
         } else {
             const int rank = item >> 1;
             // 3D: the upper half of the children (z = 2, 3) goes first, for the same reason
@@ -608,7 +608,7 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
     // Occlusion pre-mask.  The image changes under us (other tiles' atomicMax), so one
     // thread looks and the whole group follows its answer.
     if (t == 0) {
-        bool al = (sy >= a.row_begin) && (sy < a.row_end) && (sy % a.row_mod == a.row_rem);
+        bool al = (sy >= a.row_begin) && (sy < a.row_end) && ((sy + a.col_step * sx) % a.row_mod == a.row_rem);
         if (DIM == 3 && al && __ldcg(&a.image[img_index]) > sz) al = false;
         scratch[12] = al;
         if (!al) {
@@ -1223,16 +1223,16 @@ k_normals(const NormalsArgs a, const Mat4 mat)
     const uint64_t* const arena = a.arena;
     const uint32_t h = uint32_t(arena[0]);
     const int size = a.size;
-    const int blocks_x = size / 8;              // a warp owns an 8 x 4 pixel block
-    const int n_items = blocks_x * ((a.y_end - a.y_begin) / 4);
+    const int tps0 = size / 64;
+    const int n_items = a.n_owned * 128;        // a warp owns an 8 x 4 pixel block; 8 x 16 of them per screen tile
 
     for (;;) {
         const int item = warp_next(a.queue);
         if (item >= n_items) break;
-        const int px = (item % blocks_x) * 8 + (lane & 7);
-        const int py = a.y_begin + (item / blocks_x) * 4 + (lane >> 3);
+        const int tile = __ldg(&a.owned[item >> 7]), blk = item & 127;
+        const int px = (tile % tps0) * 64 + (blk & 7) * 8 + (lane & 7);
+        const int py = (tile / tps0) * 64 + (blk >> 3) * 4 + (lane >> 3);
         const int pxy = px + py * size;
-        if ((py >> 6) % a.row_mod != a.row_rem) continue;      // another context's tile row
         int pz = a.image[pxy];
         int tape = -1;
         if (pz != 0) {

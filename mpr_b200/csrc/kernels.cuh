@@ -30,8 +30,9 @@ struct EvalTilesArgs {
     int32_t count0;           // root level: number of tiles
     int32_t row_begin;        // root level: this context renders tile rows
     int32_t row_end;          //   [row_begin, row_end) in y (multi-GPU sharding) ...
-    int32_t row_mod;          //   ... of which only rows with y % row_mod == row_rem
+    int32_t row_mod;          //   ... of which only tiles with (y + col_step * x) % row_mod == row_rem
     int32_t row_rem;
+    int32_t col_step;
     FrameCtl* ctl;
     int32_t* queue;           // work-queue head for this launch
     int32_t level;            // 0, 1, 2 (statistics slot / overflow bit)
@@ -66,6 +67,7 @@ struct EvalRootArgs {
     int32_t row_end;
     int32_t row_mod;
     int32_t row_rem;
+    int32_t col_step;
     FrameCtl* ctl;
     const uint64_t* cells;    // the Tape's contiguous cells (header, clauses, end cell)
     const RootClause* sched;  // clauses sorted by (dependency level, opcode)
@@ -115,10 +117,8 @@ struct NormalsArgs {
     const int32_t* image;     // heightmap
     uint32_t* normals;
     int32_t size;
-    int32_t y_begin;          // pixel rows [y_begin, y_end) belong to this context ...
-    int32_t y_end;
-    int32_t row_mod;          // ... restricted to 64-px tile rows with row % row_mod == row_rem
-    int32_t row_rem;
+    const int32_t* owned;     // the 64x64-px screen tiles this context renders (y * tiles_per_side + x) ...
+    int32_t n_owned;          // ... and how many
     const TileNode* tiles0;
     const TileNode* tiles1;
     const TileNode* tiles2;

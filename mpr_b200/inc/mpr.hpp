@@ -123,7 +123,7 @@ struct Tiles {
 
 struct Context {
     Context(int32_t image_size_px) : image_size_px(image_size_px) {
-        mprb_ctx_opts opts = {-1, NUM_SUBTAPES, 0, 0, 0, 0};
+        mprb_ctx_opts opts = {-1, NUM_SUBTAPES, 0, 0, 0, 0, 0};
         mprb_ctx* c = nullptr;
         detail::check(mprb_ctx_create(image_size_px, &opts, &c), "mprb_ctx_create");
         handle.reset(c);

@@ -163,6 +163,28 @@ def test_interleaved_rows_tile_the_full_frame(model, dim, size, world):
         assert np.array_equal(nrm, full.normals())
 
 
+@pytest.mark.parametrize("model,dim,size,world", [("prospero", 2, 1024, 4), ("bear", 3, 512, 8), ("hello_world", 3, 256, 2)])
+def test_diagonal_tiles_tile_the_full_frame(model, dim, size, world):
+    """Tile-cyclic assignment (rank r owns the 64x64-px screen columns with (x + y) % world == r):
+    the parts are disjoint and their union is the single-context frame, image and normals."""
+    full, tape = render(model, dim, size)
+    img = np.zeros((size, size), dtype=np.int32)
+    nrm = np.zeros((size, size), dtype=np.uint32)
+    owner = np.kron(sharding.diagonal_owner(size, world), np.ones((64, 64), dtype=np.int64))
+    for r in range(world):
+        part = capi.Context(size, num_subtapes=SUBTAPES, **sharding.diagonal_tiles(size, world, r))
+        (part.render2D if dim == 2 else part.render3D)(tape)
+        assert not part.image()[owner != r].any()
+        img[owner == r] = part.image()[owner == r]
+        if dim == 3:
+            assert not part.normals()[owner != r].any()
+            nrm[owner == r] = part.normals()[owner == r]
+        part.close()
+    assert np.array_equal(img, full.image())
+    if dim == 3:
+        assert np.array_equal(nrm, full.normals())
+
+
 def test_arena_exhaustion_degrades_like_the_reference():
     """With a tiny arena, tiles keep their parent tape (reference context.cu:336-347); the image
     is still correct because every tape that was kept is valid for its tile."""

@@ -19,6 +19,21 @@ def test_band_rows_partition_the_image():
         sharding.band_rows(1024 + 64, 2, 0)    # 17 rows do not split in two
 
 
+def test_diagonal_tiles_partition_the_frame():
+    for size, world in [(1024, 2), (1024, 8), (4096, 8), (2048, 4), (256, 2)]:
+        owner = sharding.diagonal_owner(size, world)
+        counts = np.bincount(owner.ravel(), minlength=world)
+        assert (counts == (size // 64) ** 2 // world).all()          # equal shares: a plain all-gather works
+        for r in range(world):
+            o = sharding.diagonal_tiles(size, world, r)
+            assert o["col_step"] == 1 and o["row_mod"] == world and o["row_rem"] == r
+        # every tile row and every tile column is spread over all ranks
+        if size // 64 >= world:
+            assert all(len(set(owner[k])) == world and len(set(owner[:, k])) == world for k in range(size // 64))
+    with pytest.raises(ValueError):
+        sharding.diagonal_tiles(1024 + 64, 2, 0)
+
+
 def _worker(rank, world, port, size, full_path, out_path):
     import torch
     import torch.distributed as dist
@@ -36,6 +51,14 @@ def _worker(rank, world, port, size, full_path, out_path):
     local2 = torch.zeros_like(full)
     local2[owner == rank] = full[owner == rank]            # interleaved assignment
     ok = ok and bool(torch.equal(sharding.all_gather_cyclic(local2, size), full))
+    # tile-cyclic (diagonal) assignment, two images in one exchange
+    own = torch.from_numpy(np.kron(sharding.diagonal_owner(size, world) == rank, np.ones((64, 64), dtype=bool)))
+    second = full * 3 + 1
+    a, b = torch.where(own, full, torch.full_like(full, -7)), torch.where(own, second, torch.full_like(full, -7))
+    ex = sharding.TileExchange(size, world, "cpu", n_images=2)
+    out_a, out_b = torch.empty_like(full), torch.empty_like(full)
+    ex.gather([a, b], [out_a, out_b])
+    ok = ok and bool(torch.equal(out_a, full)) and bool(torch.equal(out_b, second))
     np.save(out_path.format(rank), np.array([ok]))
     dist.destroy_process_group()
 
