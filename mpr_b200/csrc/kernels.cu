@@ -54,8 +54,12 @@ __device__ __forceinline__ uint64_t make_jump(int32_t delta) {
     return uint64_t(OP_JUMP) | (uint64_t(uint32_t(delta)) << 32);
 }
 
-// 128-bit per-lane set of live slots, kept in four registers.
-struct SlotSet {
+// Per-lane set of live slots for the tape push.  WIDE: 128 bits in four registers (renamed
+// kernels: any slot id the reference allows).  Narrow: one register - kernels without renaming
+// only ever see tapes with at most 32 slot ids (use_remap), and the push spends a third of its
+// instructions on this set otherwise.
+template <bool WIDE> struct SlotSet;
+template <> struct SlotSet<true> {
     uint32_t w0, w1, w2, w3;
     __device__ __forceinline__ void clear() { w0 = w1 = w2 = w3 = 0; }
     __device__ __forceinline__ bool test(uint32_t s) const {
@@ -77,6 +81,13 @@ struct SlotSet {
         w2 &= (k == 2) ? m : ~0u;
         w3 &= (k == 3) ? m : ~0u;
     }
+};
+template <> struct SlotSet<false> {
+    uint32_t w0;
+    __device__ __forceinline__ void clear() { w0 = 0; }
+    __device__ __forceinline__ bool test(uint32_t s) const { return (w0 >> s) & 1u; }
+    __device__ __forceinline__ void set(uint32_t s) { w0 |= 1u << s; }
+    __device__ __forceinline__ void reset(uint32_t s) { w0 &= ~(1u << s); }
 };
 
 // a*x + b*y + c*z + d with the reference build's rounding sequence
@@ -390,7 +401,7 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
         // ---- tape push: backward mark & sweep (context.cu:323-458) ---------------------
         if (__any_sync(kFull, pushing)) {
             const int cap = a.arena_cap;
-            SlotSet live;
+            SlotSet<REMAP> live;
             live.clear();
             live.set(i_result);
             int o_idx = 0, o_off = 0;
@@ -1411,8 +1422,11 @@ int walk_rows(int n_slots) {
 // Renaming pays once per-id rows would leave fewer than ~24 warps per SM.
 bool use_remap(int n_slots) {
     static const char* force = getenv("MPRB_REMAP");
+    // Kernels without renaming index a 32-bit live set by slot id (SlotSet<false>): renaming is
+    // mandatory above 32 slots, whatever MPRB_REMAP says.
+    if (n_slots > 32) return true;
     if (force) return force[0] == '1';
-    return n_slots > 36;
+    return false;
 }
 // Normal pass (float4 values, no stream): shared rows, or local memory for many slots.
 static size_t normals_smem(int n_slots, bool local) {
