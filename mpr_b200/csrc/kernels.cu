@@ -948,7 +948,7 @@ k_upsample_filled(const int32_t* __restrict__ prev, int32_t* __restrict__ image,
 //     (opcode, hints) that takes the operand from the result registers and skips the dead store;
 //     operands a clause does not use are never loaded.
 // Runs clauses starting at the cell AFTER `cp` until it meets one it does not handle - END, JUMP,
-// or a libdevice transcendental (SIN..LOG) - and returns with cp on that cell and its two words
+// or a trigonometric libdevice function (EXP and LOG are handlers: libdevice's own PTX) - and returns with cp on that cell and its two words
 // in w / imm.  `sb` is this lane's slot base in shared space (slot s at sb + 256 s).
 __device__ __forceinline__ void run_float_clauses(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
 {
@@ -960,8 +960,9 @@ __device__ __forceinline__ void run_float_clauses(uint32_t& cp, uint32_t& w, uin
 }
 
 // Opcode classes for the hints (bit i = opcode i).  FAST: handled inside the PTX loop.
-constexpr uint32_t kFastOps = 0x3fffe81cu;      // everything but END, JUMP, SIN..EXP, LOG
+constexpr uint32_t kFastOps = 0x3ffffc1cu;      // everything but END, JUMP, SIN, COS, ASIN, ACOS, ATAN
 constexpr uint32_t kUsesLhs = (1u << OP_SQUARE) | (1u << OP_SQRT) | (1u << OP_NEG) | (1u << OP_ABS) | (1u << OP_ADD_LI) |
+                              (1u << OP_EXP) | (1u << OP_LOG) |
                               (1u << OP_ADD_LR) | (1u << OP_MUL_LI) | (1u << OP_MUL_LR) | (1u << OP_MIN_LI) |
                               (1u << OP_MIN_LR) | (1u << OP_MAX_LI) | (1u << OP_MAX_LR) | (1u << OP_SUB_LI) |
                               (1u << OP_SUB_LR) | (1u << OP_DIV_LI) | (1u << OP_DIV_LR) | (1u << OP_COPY_LHS);
@@ -969,8 +970,7 @@ constexpr uint32_t kUsesRhs = (1u << OP_ADD_LR) | (1u << OP_MUL_LR) | (1u << OP_
                               (1u << OP_SUB_IR) | (1u << OP_SUB_LR) | (1u << OP_DIV_IR) | (1u << OP_DIV_LR) |
                               (1u << OP_COPY_RHS);
 static_assert(kFastOps == (((1u << 30) - 1) & ~((1u << OP_END) | (1u << OP_JUMP) | (1u << OP_SIN) | (1u << OP_COS) |
-                                               (1u << OP_ASIN) | (1u << OP_ACOS) | (1u << OP_ATAN) | (1u << OP_EXP) |
-                                               (1u << OP_LOG))), "kFastOps");
+                                               (1u << OP_ASIN) | (1u << OP_ACOS) | (1u << OP_ATAN))), "kFastOps");
 
 // Writes the forwarding hints (see tools/gen_float_loop.py) into the opcode bytes of a freshly
 // arrived raw chunk.  A hint only ever relates a cell to its neighbour in memory, and the loop
