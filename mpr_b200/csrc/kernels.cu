@@ -1091,18 +1091,18 @@ __device__ __forceinline__ float2 walk_float(TapeStream<REMAP>& ts, int tape, Sl
 
 // 2D: one warp per surviving 8x8 tile, two pixels per lane (y and y + 4).
 template <bool REMAP, bool HEAT = false>
-__global__ void __launch_bounds__(kFloatThreads)
+__global__ void __launch_bounds__(kFloatMaxThreads)
 k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = lane_id();
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(kFull, int(threadIdx.x >> 5), 0);   // via shuffle: provably warp-uniform for ptxas
     typedef TapeStream<REMAP> Stream;
     Stream ts;
     ts.init(s_dyn + warp * Stream::stride(), a.arena);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
     Slots2<REMAP> slots;
-    slots.base = smem_addr(s_dyn + kFloatWarps * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
+    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
     slots.limit = uint32_t(n_rows) * 256u;
     const uint64_t* const arena = a.arena;
     unsigned long long st_tiles = 0, st_cells = 0;
@@ -1153,18 +1153,18 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 // list is roughly front-to-back and the per-lane early-out below (the
 // reference's, context.cu:852-864) culls most of what lies behind the surface.
 template <bool REMAP, bool HEAT = false>
-__global__ void __launch_bounds__(kFloatThreads)
+__global__ void __launch_bounds__(kFloatMaxThreads)
 k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = lane_id();
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(kFull, int(threadIdx.x >> 5), 0);   // via shuffle: provably warp-uniform for ptxas
     typedef TapeStream<REMAP> Stream;
     Stream ts;
     ts.init(s_dyn + warp * Stream::stride(), a.arena);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
     Slots2<REMAP> slots;
-    slots.base = smem_addr(s_dyn + kFloatWarps * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
+    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
     slots.limit = uint32_t(n_rows) * 256u;
     const uint64_t* const arena = a.arena;
     unsigned long long st_tiles = 0, st_cells = 0;
@@ -1419,6 +1419,28 @@ int walk_rows(int n_slots) {
     const int rows = env ? atoi(env) : kRemapRowsDefault;
     return rows < kRemapRowsMin ? kRemapRowsMin : (rows > 128 ? 128 : rows);
 }
+// Warps per CTA of the float pass: the shape that keeps the most warps resident per SM given the
+// per-warp shared memory (value rows + chunk stream), 1 KB the driver reserves per CTA, and the
+// limits of 32 CTAs / 64 warps per SM.  MPRB_FLOAT_WARPS overrides.
+int float_warps(int n_slots) {
+    static const char* env = getenv("MPRB_FLOAT_WARPS");
+    if (env) { const int v = atoi(env); return v < 1 ? 1 : (v > 32 ? 32 : v); }
+    static int smem_per_sm = 0;
+    if (!smem_per_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    }
+    const size_t per_warp = walk_smem(walk_rows(n_slots), use_remap(n_slots), 1);
+    int best = 1, best_resident = 0;
+    for (int w = 1; w <= kFloatMaxThreads / 32; ++w) {
+        int ctas = int(size_t(smem_per_sm) / (w * per_warp + 1024));
+        if (ctas > 32) ctas = 32;
+        if (ctas > 64 / w) ctas = 64 / w;
+        if (ctas * w > best_resident) { best_resident = ctas * w; best = w; }
+    }
+    return best;
+}
 // Renaming pays once per-id rows would leave fewer than ~24 warps per SM.
 bool use_remap(int n_slots) {
     static const char* force = getenv("MPRB_REMAP");
@@ -1521,22 +1543,24 @@ void launch_upsample_filled(int dim, const int32_t* prev, int32_t* image, int si
 
 void launch_eval_pixels(const EvalVoxelsArgs& a, const Mat3& mat, int grid, cudaStream_t s) {
     const bool local = use_remap(a.n_slots);
-    const size_t smem = walk_smem(a.n_rows, local, kFloatWarps);
+    const int fw = float_warps(a.n_slots);
+    const size_t smem = walk_smem(a.n_rows, local, fw);
     if (a.heat) {
-        if (local) k_eval_pixels<true, true><<<grid, kFloatThreads, smem, s>>>(a, mat);
-        else k_eval_pixels<false, true><<<grid, kFloatThreads, smem, s>>>(a, mat);
-    } else if (local) k_eval_pixels<true><<<grid, kFloatThreads, smem, s>>>(a, mat);
-    else k_eval_pixels<false><<<grid, kFloatThreads, smem, s>>>(a, mat);
+        if (local) k_eval_pixels<true, true><<<grid, fw * 32, smem, s>>>(a, mat);
+        else k_eval_pixels<false, true><<<grid, fw * 32, smem, s>>>(a, mat);
+    } else if (local) k_eval_pixels<true><<<grid, fw * 32, smem, s>>>(a, mat);
+    else k_eval_pixels<false><<<grid, fw * 32, smem, s>>>(a, mat);
 }
 
 void launch_eval_voxels(const EvalVoxelsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
     const bool local = use_remap(a.n_slots);
-    const size_t smem = walk_smem(a.n_rows, local, kFloatWarps);
+    const int fw = float_warps(a.n_slots);
+    const size_t smem = walk_smem(a.n_rows, local, fw);
     if (a.heat) {
-        if (local) k_eval_voxels<true, true><<<grid, kFloatThreads, smem, s>>>(a, mat);
-        else k_eval_voxels<false, true><<<grid, kFloatThreads, smem, s>>>(a, mat);
-    } else if (local) k_eval_voxels<true><<<grid, kFloatThreads, smem, s>>>(a, mat);
-    else k_eval_voxels<false><<<grid, kFloatThreads, smem, s>>>(a, mat);
+        if (local) k_eval_voxels<true, true><<<grid, fw * 32, smem, s>>>(a, mat);
+        else k_eval_voxels<false, true><<<grid, fw * 32, smem, s>>>(a, mat);
+    } else if (local) k_eval_voxels<true><<<grid, fw * 32, smem, s>>>(a, mat);
+    else k_eval_voxels<false><<<grid, fw * 32, smem, s>>>(a, mat);
 }
 
 void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
@@ -1579,9 +1603,10 @@ int occupancy_eval_tiles(int dim, bool root, int n_slots) {
 
 int occupancy_eval_voxels(int dim, int n_slots) {
     const bool local = use_remap(n_slots);
-    const size_t smem = walk_smem(walk_rows(n_slots), local, kFloatWarps);
-    if (dim == 3) return local ? occ(k_eval_voxels<true>, smem, kFloatThreads) : occ(k_eval_voxels<false>, smem, kFloatThreads);
-    return local ? occ(k_eval_pixels<true>, smem, kFloatThreads) : occ(k_eval_pixels<false>, smem, kFloatThreads);
+    const int fw = float_warps(n_slots);
+    const size_t smem = walk_smem(walk_rows(n_slots), local, fw);
+    if (dim == 3) return local ? occ(k_eval_voxels<true>, smem, fw * 32) : occ(k_eval_voxels<false>, smem, fw * 32);
+    return local ? occ(k_eval_pixels<true>, smem, fw * 32) : occ(k_eval_pixels<false>, smem, fw * 32);
 }
 
 int occupancy_normals(int n_slots) {

@@ -8,11 +8,11 @@
 namespace mprb {
 
 constexpr int kEvalWarps = 4;                 // warps per CTA: interval and normal passes
-// The float pass runs ONE warp per CTA: everything warp-uniform (clause words, tape pointers) is
-// then CTA-uniform, which lets ptxas drop most of the divergence bookkeeping in the clause loop
-// (-5 % on bear); the other passes lose more from the 32-CTA/SM limit than they gain.
-constexpr int kFloatWarps = 1;
-constexpr int kFloatThreads = kFloatWarps * 32;
+// The float pass picks its CTA size at launch (float_warps): the CTA shape that packs the most
+// warps into an SM's shared memory, e.g. 2 x 17 warps for bear's 23 slot rows.  The warp index is
+// taken through a shuffle, which ptxas knows to be warp-uniform, so clause decode still runs on
+// the uniform datapath whatever the CTA size.
+constexpr int kFloatMaxThreads = 1024;
 constexpr int kEvalThreads = kEvalWarps * 32;
 
 struct EvalTilesArgs {
@@ -142,6 +142,7 @@ void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_
 
 // Resident CTAs per SM for a given slot count (sizes the persistent grids).
 int walk_rows(int n_slots);
+int float_warps(int n_slots);
 int occupancy_eval_tiles(int dim, bool root, int n_slots);
 int occupancy_eval_voxels(int dim, int n_slots);
 int occupancy_normals(int n_slots);
