@@ -169,6 +169,71 @@ template <> struct MatOf<3> { typedef Mat4 type; };
 
 }  // namespace
 
+// Opcode classes for the hints (bit i = opcode i).  FAST: handled inside the PTX loop.
+constexpr uint32_t kFastOps = 0x3ffffc1cu;      // everything but END, JUMP, SIN, COS, ASIN, ACOS, ATAN
+constexpr uint32_t kUsesLhs = (1u << OP_SQUARE) | (1u << OP_SQRT) | (1u << OP_NEG) | (1u << OP_ABS) | (1u << OP_ADD_LI) |
+                              (1u << OP_EXP) | (1u << OP_LOG) |
+                              (1u << OP_ADD_LR) | (1u << OP_MUL_LI) | (1u << OP_MUL_LR) | (1u << OP_MIN_LI) |
+                              (1u << OP_MIN_LR) | (1u << OP_MAX_LI) | (1u << OP_MAX_LR) | (1u << OP_SUB_LI) |
+                              (1u << OP_SUB_LR) | (1u << OP_DIV_LI) | (1u << OP_DIV_LR) | (1u << OP_COPY_LHS);
+constexpr uint32_t kUsesRhs = (1u << OP_ADD_LR) | (1u << OP_MUL_LR) | (1u << OP_MIN_LR) | (1u << OP_MAX_LR) |
+                              (1u << OP_SUB_IR) | (1u << OP_SUB_LR) | (1u << OP_DIV_IR) | (1u << OP_DIV_LR) |
+                              (1u << OP_COPY_RHS);
+static_assert(kFastOps == (((1u << 30) - 1) & ~((1u << OP_END) | (1u << OP_JUMP) | (1u << OP_SIN) | (1u << OP_COS) |
+                                               (1u << OP_ASIN) | (1u << OP_ACOS) | (1u << OP_ATAN))), "kFastOps");
+
+// Writes the forwarding hints (see tools/gen_float_loop.py, gen_interval_loop.py) into the opcode
+// bytes of a freshly arrived raw chunk; FAST / LHS / RHS are the opcode classes of the loop that
+// will run it.  A hint only ever relates a cell to its neighbour in memory, and the loop
+// only ever runs a cell right after that neighbour (entries land after an END / JUMP / slow
+// cell, which never forward), so stale cells elsewhere in the chunk do not matter.
+template <uint32_t FAST, uint32_t LHS, uint32_t RHS>
+__device__ __forceinline__ void annotate_chunk(uint32_t buf)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t byte0[2];
+    #pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int j = lane + 32 * k;
+        const uint32_t w = lds_u32(buf + j * 8);
+        const uint32_t wp = j > 0 ? lds_u32(buf + (j - 1) * 8) : 0u;
+        const uint32_t wn = j < kChunk - 1 ? lds_u32(buf + (j + 1) * 8) : 0u;
+        auto fast = [](uint32_t x) { return (x & 0xe0u) == 0 && ((FAST >> (x & 31u)) & 1u); };
+        const uint32_t op = w & 31u;
+        const uint32_t prev_out = (wp >> 8) & 0xff;
+        uint32_t flags = 0;
+        if (fast(w)) {
+            if (fast(wp)) {
+                if (((LHS >> op) & 1u) && ((w >> 16) & 0xff) == prev_out) flags |= 0x20;
+                if (((RHS >> op) & 1u) && (w >> 24) == prev_out) flags |= 0x40;
+            }
+            if (fast(wn) && ((wn >> 8) & 0xff) == ((w >> 8) & 0xff)) flags |= 0x80;
+        }
+        byte0[k] = (w & 0xff) | flags;
+    }
+    __syncwarp();
+    sts_u8(buf + lane * 8, byte0[0]);
+    sts_u8(buf + (lane + 32) * 8, byte0[1]);
+    __syncwarp();
+}
+
+// Opcode classes of the interval loop (tools/gen_interval_loop.py prints them).
+constexpr uint32_t kIvFastOps = 0x39ffec7cu, kIvUsesLhs = 0x11bfec1cu, kIvUsesRhs = 0x20d54000u;
+
+// The forward clause loop of the interval pass in PTX (generated: tools/gen_interval_loop.py ->
+// interval_loop_ptx.inc); same scheme as run_float_clauses below.  Runs clauses from the cell after
+// `cp` until one it does not handle (END, JUMP, DIV_IMM_RHS, DIV_LHS_RHS, ASIN, ACOS, ATAN, LOG) and
+// returns with cp on that cell; min / max verdicts are recorded into cw / choices[] on the way.
+__device__ __forceinline__ void run_interval_clauses(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb, uint32_t& cw,
+                                                     uint32_t& n_choice, uint32_t& any_choice, const uint32_t* choices)
+{
+    asm volatile(
+#include "interval_loop_ptx.inc"
+        : "+r"(cp), "=&r"(w), "=&r"(imm), "+r"(cw), "+r"(n_choice), "+r"(any_choice)
+        : "r"(sb), "l"(choices)
+        : "memory");
+}
+
 ////////////////////////////////////////////////////////////////////////////////
 // Interval pass
 
@@ -292,24 +357,30 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
         // ---- forward walk (context.cu:223-287) -------------------------------------
         // Every 64-cell chunk ends in a JUMP or the end cell (see tape_stream.cuh), so the hot
         // path is a running shared-memory pointer; chunk switches happen only at JUMP cells.
-        ts.fetch(tape);
+        // Without slot renaming the loop proper is generated PTX (run_interval_clauses): it comes
+        // back here only for END / JUMP and the few opcodes it leaves to the C++ switch below.
+        if (ts.fetch(tape) && !REMAP) annotate_chunk<kIvFastOps, kIvUsesLhs, kIvUsesRhs>(ts.buf);
         uint32_t cp = ts.rd + ((tape & (kChunk - 1)) << 3);
         uint32_t seg = cp;         // where the current chunk segment started (for statistics)
-        int n_choice = 0;          // warp-uniform: how many min/max clauses seen so far
+        uint32_t n_choice = 0;     // warp-uniform: how many min/max clauses seen so far
         uint32_t cw = 0;           // verdict word under construction
-        bool any_choice = false;
+        uint32_t any_choice = 0;   // nonzero once a min/max was decided for this lane's tile
         unsigned cells = 0;
         uint2 d;
         for (;;) {
-            cp += 8;
-            d = lds_u2(cp);
+            if (REMAP) {
+                cp += 8;
+                d = lds_u2(cp);
+            } else {
+                run_interval_clauses(cp, d.x, d.y, slots.base, cw, n_choice, any_choice, choices);
+            }
             const uint32_t w = d.x;
             const uint32_t op = w & 0xff;
             if (op <= OP_JUMP) {
                 cells += (cp - seg) >> 3;
                 if (op == OP_END) { --cells; break; }
                 const int t = ts.base + int((cp - ts.rd) >> 3) + int32_t(d.y);
-                ts.fetch(t);
+                if (ts.fetch(t) && !REMAP) annotate_chunk<kIvFastOps, kIvUsesLhs, kIvUsesRhs>(ts.buf);
                 cp = ts.rd + ((t & (kChunk - 1)) << 3);
                 seg = cp;
                 continue;
@@ -318,6 +389,19 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
             const ival L = slots.ld(off_lhs2(w));
             const ival R = slots.ld(off_rhs2(w));
             ival o;
+            if (!REMAP) {
+                // the opcodes the PTX loop hands back
+                switch (op) {
+                    case OP_ASIN:   o = iv_asin(L); break;
+                    case OP_ACOS:   o = iv_acos(L); break;
+                    case OP_ATAN:   o = iv_atan(L); break;
+                    case OP_LOG:    o = iv_log(L); break;
+                    case OP_DIV_IR: o = iv_div(imm, R); break;
+                    default:        o = iv_div(L, R); break;      // OP_DIV_LR
+                }
+                slots.st(off_out2(w), o);
+                continue;
+            }
             int c = 0;
             switch (op) {
                 case OP_SQUARE: o = iv_square(L); break;
@@ -358,7 +442,7 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                     cw = 0;
                 }
                 ++n_choice;
-                any_choice |= (c != 0);
+                any_choice |= uint32_t(c);
             }
             slots.st(off_out2(w), o);
         }
@@ -381,7 +465,7 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                 else a.image[img_index] = 1;
             } else {
                 out_position = position;
-                pushing = any_choice;
+                pushing = any_choice != 0;
             }
         }
         int out_tape = tape;
@@ -431,7 +515,9 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                 cp -= 8;
                 b = lds_u2(cp);
                 const uint32_t w = b.x;
-                const uint32_t op = w & 0xff;
+                // Without renaming the chunk may carry the forward loop's hint bits (bits 5-7 of
+                // the opcode byte, annotate_chunk): they are not part of the tape.
+                const uint32_t op = REMAP ? (w & 0xff) : (w & 0x1f);
                 if (op <= OP_JUMP) {
                     bcells += (seg - cp) >> 3;
                     if (op == OP_END) { --bcells; break; }
@@ -481,7 +567,7 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                     } else {
                         live.reset(i_out);
                         const uint2 raw = lds_u2(ts.buf + (cp - ts.rd));     // cell as stored (ids, not rows)
-                        const uint64_t d64 = uint64_t(raw.x) | (uint64_t(raw.y) << 32);
+                        const uint64_t d64 = uint64_t(REMAP ? raw.x : (raw.x & ~0xe0u)) | (uint64_t(raw.y) << 32);
                         uint64_t e = d64;
                         bool emit = true;
                         if (choice == 0) {
@@ -959,52 +1045,6 @@ __device__ __forceinline__ void run_float_clauses(uint32_t& cp, uint32_t& w, uin
         : "memory");
 }
 
-// Opcode classes for the hints (bit i = opcode i).  FAST: handled inside the PTX loop.
-constexpr uint32_t kFastOps = 0x3ffffc1cu;      // everything but END, JUMP, SIN, COS, ASIN, ACOS, ATAN
-constexpr uint32_t kUsesLhs = (1u << OP_SQUARE) | (1u << OP_SQRT) | (1u << OP_NEG) | (1u << OP_ABS) | (1u << OP_ADD_LI) |
-                              (1u << OP_EXP) | (1u << OP_LOG) |
-                              (1u << OP_ADD_LR) | (1u << OP_MUL_LI) | (1u << OP_MUL_LR) | (1u << OP_MIN_LI) |
-                              (1u << OP_MIN_LR) | (1u << OP_MAX_LI) | (1u << OP_MAX_LR) | (1u << OP_SUB_LI) |
-                              (1u << OP_SUB_LR) | (1u << OP_DIV_LI) | (1u << OP_DIV_LR) | (1u << OP_COPY_LHS);
-constexpr uint32_t kUsesRhs = (1u << OP_ADD_LR) | (1u << OP_MUL_LR) | (1u << OP_MIN_LR) | (1u << OP_MAX_LR) |
-                              (1u << OP_SUB_IR) | (1u << OP_SUB_LR) | (1u << OP_DIV_IR) | (1u << OP_DIV_LR) |
-                              (1u << OP_COPY_RHS);
-static_assert(kFastOps == (((1u << 30) - 1) & ~((1u << OP_END) | (1u << OP_JUMP) | (1u << OP_SIN) | (1u << OP_COS) |
-                                               (1u << OP_ASIN) | (1u << OP_ACOS) | (1u << OP_ATAN))), "kFastOps");
-
-// Writes the forwarding hints (see tools/gen_float_loop.py) into the opcode bytes of a freshly
-// arrived raw chunk.  A hint only ever relates a cell to its neighbour in memory, and the loop
-// only ever runs a cell right after that neighbour (entries land after an END / JUMP / slow
-// cell, which never forward), so stale cells elsewhere in the chunk do not matter.
-__device__ __forceinline__ void annotate_chunk(uint32_t buf)
-{
-    const int lane = threadIdx.x & 31;
-    uint32_t byte0[2];
-    #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int j = lane + 32 * k;
-        const uint32_t w = lds_u32(buf + j * 8);
-        const uint32_t wp = j > 0 ? lds_u32(buf + (j - 1) * 8) : 0u;
-        const uint32_t wn = j < kChunk - 1 ? lds_u32(buf + (j + 1) * 8) : 0u;
-        auto fast = [](uint32_t x) { return (x & 0xe0u) == 0 && ((kFastOps >> (x & 31u)) & 1u); };
-        const uint32_t op = w & 31u;
-        const uint32_t prev_out = (wp >> 8) & 0xff;
-        uint32_t flags = 0;
-        if (fast(w)) {
-            if (fast(wp)) {
-                if (((kUsesLhs >> op) & 1u) && ((w >> 16) & 0xff) == prev_out) flags |= 0x20;
-                if (((kUsesRhs >> op) & 1u) && (w >> 24) == prev_out) flags |= 0x40;
-            }
-            if (fast(wn) && ((wn >> 8) & 0xff) == ((w >> 8) & 0xff)) flags |= 0x80;
-        }
-        byte0[k] = (w & 0xff) | flags;
-    }
-    __syncwarp();
-    sts_u8(buf + lane * 8, byte0[0]);
-    sts_u8(buf + (lane + 32) * 8, byte0[1]);
-    __syncwarp();
-}
-
 // One clause in C++ (context.cu:887-920): the slot-renaming variant runs every clause through
 // this, the PTX loop above only the transcendental ones.
 __device__ __forceinline__ float2 float_clause(uint32_t op, float2 L, float2 R, float imm)
@@ -1057,7 +1097,7 @@ __device__ __forceinline__ float2 float_clause_libdevice(uint32_t op, float2 L)
 template <bool REMAP>
 __device__ __forceinline__ float2 walk_float(TapeStream<REMAP>& ts, int tape, Slots2<REMAP>& slots, unsigned& cells)
 {
-    if (ts.fetch(tape) && !REMAP) annotate_chunk(ts.buf);
+    if (ts.fetch(tape) && !REMAP) annotate_chunk<kFastOps, kUsesLhs, kUsesRhs>(ts.buf);
     uint32_t cp = ts.rd + ((tape & (kChunk - 1)) << 3);
     uint32_t seg = cp;
     uint32_t w, immb;
@@ -1075,7 +1115,7 @@ __device__ __forceinline__ float2 walk_float(TapeStream<REMAP>& ts, int tape, Sl
             cells += (cp - seg) >> 3;
             if (op == OP_END) { --cells; break; }
             const int t = ts.base + int((cp - ts.rd) >> 3) + int32_t(immb);
-            if (ts.fetch(t) && !REMAP) annotate_chunk(ts.buf);
+            if (ts.fetch(t) && !REMAP) annotate_chunk<kFastOps, kUsesLhs, kUsesRhs>(ts.buf);
             cp = ts.rd + ((t & (kChunk - 1)) << 3);
             seg = cp;
             continue;
