@@ -191,3 +191,46 @@ def test_dump_tape_reproduces_the_kernel_libfive_generated_for_brute_cu():
         "x + 0.500000f", "v0 * v0", "y * y", "z * z", "v2 + v3", "v1 + v4", "sqrt(v5)", "v6 - 0.250000f",
         "x - 0.500000f", "v8 * v8", "v9 + v4", "sqrt(v10)", "v11 - 0.250000f", "min(v7, v12)"]
     assert "if (v13 < 0.0f)" in re.sub(r"v\d+", lambda k: names.get(k.group(0), k.group(0)), out)
+
+
+def test_generated_ptx_loops_are_current_and_cover_the_opcode_table(tmp_path):
+    """csrc/float_loop_ptx.inc and interval_loop_ptx.inc are generated (tools/gen_*_loop.py): the
+    committed files must be what the generators emit, every dispatch table must have 256 entries,
+    and the opcode classes kernels.cu feeds the annotation pass must be the generators'."""
+    import importlib.util
+    src = (ROOT / "mpr_b200" / "csrc" / "kernels.cu").read_text()
+    for tool, inc in (("gen_float_loop", "float_loop_ptx.inc"), ("gen_interval_loop", "interval_loop_ptx.inc")):
+        spec = importlib.util.spec_from_file_location(tool, ROOT / "tools" / f"{tool}.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        path = ROOT / "mpr_b200" / "csrc" / inc
+        before = path.read_text()
+        mod.main()
+        assert path.read_text() == before, f"{inc} is stale: run tools/{tool}.py"
+        i = before.index(".branchtargets")
+        assert before[i:before.index(";", i)].count("_%=") == 256
+        fast = sum(1 << o for o in mod.OPS)
+        assert f"0x{fast:08x}u" in src, (tool, hex(fast))
+    # every handler the table names is defined exactly once
+    for inc in ("float_loop_ptx.inc", "interval_loop_ptx.inc"):
+        text = (ROOT / "mpr_b200" / "csrc" / inc).read_text()
+        names = set(re.findall(r"(H\d+_\d{3})_%=", text[text.index(".branchtargets"):text.index("LOOP_%=:")]))
+        for n in names:
+            assert len(re.findall(rf'"{n}_%=:', text)) == 1, n
+
+
+def test_interval_multiply_operand_selection_matches_the_nine_case_table():
+    """The MUL_LHS_RHS handler of the PTX interval loop picks its four operands with predicate
+    algebra; the table it must equal is iv_mul in csrc/ival.cuh (reference gpu_interval.hpp:85-146)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_interval_loop", ROOT / "tools" / "gen_interval_loop.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    # (class a, class b) -> (lower: a?, b?; upper: a?, b?); class bit0 = lo < 0, bit1 = hi > 0
+    table = {(3, 1): ("ah", "bl", "al", "bl"), (3, 2): ("al", "bh", "ah", "bh"),
+             (1, 3): ("al", "bh", "al", "bl"), (1, 1): ("ah", "bh", "al", "bl"), (1, 2): ("al", "bh", "ah", "bl"),
+             (2, 3): ("ah", "bl", "ah", "bh"), (2, 1): ("ah", "bl", "al", "bh"), (2, 2): ("al", "bl", "ah", "bh")}
+    for (ca, cb), want in table.items():
+        s = mod.mul_select(bool(ca & 1), bool(ca & 2), bool(cb & 1), bool(cb & 2))
+        got = ("ah" if s[0] else "al", "bl" if s[1] else "bh", "al" if s[2] else "ah", "bl" if s[3] else "bh")
+        assert got == want, (ca, cb)
