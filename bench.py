@@ -175,7 +175,9 @@ def run_mine(args, workloads):
                 ptr, nbytes = ctx.device_normals()
                 job["dev_nrm"] = torch.as_tensor(DevArray(ptr, size * size, "<i4"), device=f"cuda:{local}").view(size, size)
             if SHARD == "diag":
-                job["exchange"] = sharding.TileExchange(size, world, f"cuda:{local}", n_images=2 if dim == 3 else 1)
+                # a 2D frame is 0/1 and depth < size: they cross NVLink as uint8 / int16 (normals stay 32 bit)
+                job["exchange"] = sharding.TileExchange(size, world, f"cuda:{local}", n_images=2 if dim == 3 else 1,
+                                                        narrow=[2, 4] if dim == 3 else [1])
         jobs.append(job)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2

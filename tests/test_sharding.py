@@ -59,6 +59,13 @@ def _worker(rank, world, port, size, full_path, out_path):
     out_a, out_b = torch.empty_like(full), torch.empty_like(full)
     ex.gather([a, b], [out_a, out_b])
     ok = ok and bool(torch.equal(out_a, full)) and bool(torch.equal(out_b, second))
+    # narrow transport: a 0/1 image as bytes, a depth-like image as int16, a full-width one beside them
+    depth = (full * 517 + 3) % 1024
+    wide = full * 0x01010101 - 5
+    ex = sharding.TileExchange(size, world, "cpu", n_images=3, narrow=[1, 2, 4])
+    outs = [torch.empty_like(full) for _ in range(3)]
+    ex.gather([torch.where(own, x, torch.zeros_like(x)) for x in (full, depth, wide)], outs)
+    ok = ok and all(bool(torch.equal(o, x)) for o, x in zip(outs, (full, depth, wide)))
     np.save(out_path.format(rank), np.array([ok]))
     dist.destroy_process_group()
 
