@@ -1335,9 +1335,16 @@ k_normals(const NormalsArgs a, const Mat4 mat)
             slots.st(off_rhs2(h), sz_);
             bool active = tape >= 0;
             int pos = active ? tape : 0;
+            // The walk is a chain of dependent loads (clause -> operands -> next clause) with few
+            // warps to hide it, so the NEXT clause is fetched while this one runs; only a JUMP
+            // (one per 62 cells) invalidates the prefetch.  The arena has a chunk of slack behind
+            // it, so reading one cell past an END cell is in bounds.
+            uint64_t ahead = __ldg(&arena[pos + 1]);
             while (__any_sync(kFull, active)) {
                 if (active) {
-                    const uint64_t d = __ldg(&arena[++pos]);
+                    const uint64_t d = ahead;
+                    ++pos;
+                    ahead = __ldg(&arena[pos + 1]);
                     const uint32_t w = uint32_t(d);
                     const uint32_t op = w & 0xff;
                     if (op == OP_END) {
@@ -1345,6 +1352,7 @@ k_normals(const NormalsArgs a, const Mat4 mat)
                         active = false;
                     } else if (op == OP_JUMP) {
                         pos += int32_t(d >> 32);
+                        ahead = __ldg(&arena[pos + 1]);
                         ++my_cells;
                     } else {
                         ++my_cells;
