@@ -1,6 +1,7 @@
 """Per-kernel CUDA-event times of this repository's frames (no reference arm): quick A/B tool.
 usage: python tools/kernel_times.py [model:dim:size ...]   -> gpurun_out/kernel_times.json"""
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -26,7 +27,12 @@ def main():
     for case in cases:
         model, dim, size = case.split(":")
         dim, size = int(dim), int(size)
-        ctx = capi.Context(size, num_subtapes=6400000)
+        shard = {}
+        if os.environ.get("MPRB_KT_SHARD"):                   # "world:rank": time one rank's share on one GPU
+            from mpr_b200 import sharding
+            world, rank = map(int, os.environ["MPRB_KT_SHARD"].split(":"))
+            shard = sharding.diagonal_tiles(size, world, rank)
+        ctx = capi.Context(size, num_subtapes=6400000, **shard)
         tape = capi.Tape(parity.load_tape(model))
         render = (lambda: ctx.render2D(tape)) if dim == 2 else (lambda: ctx.render3D(tape))
         for _ in range(5):
