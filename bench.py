@@ -176,8 +176,7 @@ def run_mine(args, workloads):
                 job["dev_nrm"] = torch.as_tensor(DevArray(ptr, size * size, "<i4"), device=f"cuda:{local}").view(size, size)
             if SHARD == "diag":
                 # a 2D frame is 0/1 and depth < size: they cross NVLink as uint8 / int16 (normals stay 32 bit)
-                job["exchange"] = sharding.TileExchange(size, world, f"cuda:{local}", n_images=2 if dim == 3 else 1,
-                                                        narrow=[2, 4] if dim == 3 else [1])
+                job["exchange"] = sharding.NativeExchange(ctx, dim, world, f"cuda:{local}")
         jobs.append(job)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
@@ -190,8 +189,7 @@ def run_mine(args, workloads):
         e0.record()
         if SHARD == "diag":
             # tile-cyclic: depth and normals blocks travel in ONE all-gather; every rank ends up with the full frame
-            imgs = [job["dev_img"]] + ([job["dev_nrm"]] if job["dim"] == 3 else [])
-            job["exchange"].gather(imgs, imgs)
+            job["exchange"].gather()
         else:
             # interleaved tile rows -> one all-gather per image
             job["dev_img"].copy_(sharding.all_gather_cyclic(job["dev_img"], job["size"]))

@@ -134,6 +134,18 @@ int mprb_render2d_heatmap(mprb_ctx* ctx, const mprb_tape* tape, const float mat3
 int mprb_render3d_heatmap(mprb_ctx* ctx, const mprb_tape* tape, const float mat4_colmajor[16],
                           float** heatmap_out);
 
+/* ---- multi-GPU exchange helpers (no reference counterpart; the reference is single-GPU) ---- */
+/* For contexts created with row_mod = world > 1 over the whole frame (row_begin = 0, row_end = all,
+ * tiles per side divisible by world).  After a frame, mprb_exchange_pack writes the 64x64-px blocks
+ * this context owns - depth narrowed to uint8 (2D) / int16 (3D), then the normals in 3D - into
+ * `dst_device` (mprb_exchange_bytes bytes); all-gather those buffers in rank order (NCCL, MPI, ...)
+ * and hand the result to mprb_exchange_unpack, which scatters every rank's blocks into this
+ * context's full-size image and normals.  `stream` is a cudaStream_t (NULL = the context's own);
+ * the calls are asynchronous on it.  dim = 2 or 3: the kind of frame last rendered. */
+size_t mprb_exchange_bytes(const mprb_ctx* ctx, int dim);
+int mprb_exchange_pack(mprb_ctx* ctx, int dim, void* dst_device, void* stream);
+int mprb_exchange_unpack(mprb_ctx* ctx, int dim, const void* src_device, void* stream);
+
 /* ---- post-effects: mpr::Effects (inc/effects.hpp:21-37, src/effects.cu:229-297) ---- */
 typedef struct mprb_effects mprb_effects;
 /* ssao_kernel: 64x3, ssao_rvecs: 256x3, both column-major floats (the Eigen members the

@@ -82,7 +82,7 @@ EXPORTS = [
     "mprb_render3d_host", "mprb_frame_stats_get", "mprb_tape_from_frep", "mprb_free", "mprb_free_device",
     "mprb_last_error", "mprb_version", "mprb_effects_create", "mprb_effects_destroy",
     "mprb_effects_draw_ssao", "mprb_effects_draw_shaded", "mprb_effects_buffers",
-    "mprb_malloc_managed", "mprb_render2d_brute", "mprb_render2d_heatmap", "mprb_render3d_heatmap",
+    "mprb_malloc_managed", "mprb_exchange_bytes", "mprb_exchange_pack", "mprb_exchange_unpack", "mprb_render2d_brute", "mprb_render2d_heatmap", "mprb_render3d_heatmap",
 ]
 
 _lib = None
@@ -125,6 +125,10 @@ def lib():
     L.mprb_render2d_brute.argtypes = [vp, vp, C.c_void_p, C.c_float]
     L.mprb_render2d_heatmap.argtypes = [vp, vp, C.c_void_p, C.c_float, C.POINTER(C.POINTER(C.c_float))]
     L.mprb_render3d_heatmap.argtypes = [vp, vp, C.c_void_p, C.POINTER(C.POINTER(C.c_float))]
+    L.mprb_exchange_bytes.argtypes = [vp, C.c_int]
+    L.mprb_exchange_bytes.restype = C.c_size_t
+    L.mprb_exchange_pack.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p]
+    L.mprb_exchange_unpack.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p]
     L.mprb_effects_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(vp)]
     L.mprb_effects_destroy.argtypes = [vp]
     L.mprb_effects_destroy.restype = None
@@ -306,6 +310,15 @@ class Context:
         h = C.POINTER(C.c_float)()
         _check(lib().mprb_render3d_heatmap(self._h, tape._h, m.ctypes.data, C.byref(h)))
         return self._take_heatmap(h)
+
+    def exchange_bytes(self, dim: int) -> int:
+        return int(lib().mprb_exchange_bytes(self._h, dim))
+
+    def exchange_pack(self, dim: int, dst_ptr: int, stream: int = 0):
+        _check(lib().mprb_exchange_pack(self._h, dim, dst_ptr, stream))
+
+    def exchange_unpack(self, dim: int, src_ptr: int, stream: int = 0):
+        _check(lib().mprb_exchange_unpack(self._h, dim, src_ptr, stream))
 
     def render2D_host(self, cells: np.ndarray, image_out: np.ndarray, mat=None, z: float = 0.0):
         m = mat_colmajor(np.eye(3) if mat is None else mat)

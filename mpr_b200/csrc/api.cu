@@ -843,6 +843,40 @@ int mprb_render3d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
     return finish(c, 3);
 }
 
+static int exchange_check(const mprb_ctx* c, int dim) {
+    if (!c) return fail(MPRB_E_ARG, "null context");
+    if (dim != 2 && dim != 3) return fail(MPRB_E_ARG, "dim must be 2 or 3");
+    const int tiles = c->size / 64;
+    if (c->row_mod <= 1 || c->row_begin != 0 || c->row_end != tiles || tiles % c->row_mod != 0)
+        return fail(MPRB_E_ARG, "exchange needs row_mod = world > 1 over the whole frame, tiles per side divisible by world");
+    return MPRB_OK;
+}
+
+size_t mprb_exchange_bytes(const mprb_ctx* c, int dim) {
+    if (exchange_check(c, dim)) return 0;
+    return exchange_rank_bytes(c->size, c->row_mod, dim);
+}
+
+int mprb_exchange_pack(mprb_ctx* c, int dim, void* dst, void* stream) {
+    if (int e = exchange_check(c, dim)) return e;
+    if (!dst) return fail(MPRB_E_ARG, "null buffer");
+    MPRB_CUDA(cudaSetDevice(c->device));
+    launch_exchange(true, c->size, c->row_mod, c->row_rem, c->col_step, dim, c->filled[3], c->normals, dst,
+                    stream ? cudaStream_t(stream) : c->stream);
+    MPRB_CUDA(cudaGetLastError());
+    return MPRB_OK;
+}
+
+int mprb_exchange_unpack(mprb_ctx* c, int dim, const void* src, void* stream) {
+    if (int e = exchange_check(c, dim)) return e;
+    if (!src) return fail(MPRB_E_ARG, "null buffer");
+    MPRB_CUDA(cudaSetDevice(c->device));
+    launch_exchange(false, c->size, c->row_mod, c->row_rem, c->col_step, dim, c->filled[3], c->normals,
+                    const_cast<void*>(src), stream ? cudaStream_t(stream) : c->stream);
+    MPRB_CUDA(cudaGetLastError());
+    return MPRB_OK;
+}
+
 struct mprb_effects {
     float* kernel = nullptr;     // device, 64x3
     float* rvecs = nullptr;      // device, 256x3

@@ -9,4 +9,8 @@ void launch_draw_ssao(const int32_t* depth, const uint32_t* norm, const float* k
 void launch_blur_ssao(const int32_t* image, const int32_t* ssao, int size, int32_t* out, cudaStream_t s);
 void launch_draw_shaded(const int32_t* depth, const uint32_t* norm, const int32_t* ssao, int size, int32_t* out,
                         cudaStream_t s);
+// Multi-GPU exchange (effects.cu): bytes one rank contributes, and the pack / unpack launches.
+size_t exchange_rank_bytes(int size, int world, int dim);
+void launch_exchange(bool pack, int size, int world, int rank, int col_step, int dim, int32_t* depth, uint32_t* normals,
+                     void* buf, cudaStream_t s);
 }  // namespace mprb

@@ -147,3 +147,26 @@ class TileExchange:
         self.pack(images, dist.get_rank(group))
         dist.all_gather_into_tensor(self.recv.view(-1), self.send, group=group)
         return self.unpack(outs)
+
+
+class NativeExchange:
+    """TileExchange with the library's own pack / unpack kernels (mprb_exchange_*): one launch to
+    narrow and gather the owned blocks, one NCCL all-gather, one launch to scatter all ranks' blocks
+    into the context's full-size image and normals - in place, on the caller's CUDA stream."""
+
+    def __init__(self, ctx, dim: int, world: int, device):
+        import torch
+        self.ctx, self.dim, self.world = ctx, dim, world
+        self.bytes = ctx.exchange_bytes(dim)
+        if self.bytes == 0:
+            raise ValueError("context is not sharded over the whole frame")
+        self.send = torch.empty(self.bytes, dtype=torch.uint8, device=device)
+        self.recv = torch.empty(world * self.bytes, dtype=torch.uint8, device=device)
+
+    def gather(self, group=None):
+        import torch
+        import torch.distributed as dist
+        stream = torch.cuda.current_stream().cuda_stream
+        self.ctx.exchange_pack(self.dim, self.send.data_ptr(), stream)
+        dist.all_gather_into_tensor(self.recv, self.send, group=group)
+        self.ctx.exchange_unpack(self.dim, self.recv.data_ptr(), stream)

@@ -185,6 +185,36 @@ def test_diagonal_tiles_tile_the_full_frame(model, dim, size, world):
         assert np.array_equal(nrm, full.normals())
 
 
+@pytest.mark.parametrize("model,dim,size,world,col_step", [("prospero", 2, 1024, 4, 1), ("bear", 3, 512, 8, 1),
+                                                          ("hello_world", 3, 256, 2, 0)])
+def test_exchange_kernels_reassemble_the_frame(model, dim, size, world, col_step):
+    """mprb_exchange_pack / _unpack: every rank's packed blocks, laid end to end as an all-gather
+    would leave them, scatter back into the single-context frame (all ranks emulated on one GPU)."""
+    import torch
+    full, tape = render(model, dim, size)
+    parts = []
+    for r in range(world):
+        opts = sharding.diagonal_tiles(size, world, r) if col_step else sharding.cyclic_rows(size, world, r)
+        parts.append(capi.Context(size, num_subtapes=SUBTAPES, **opts))
+        (parts[-1].render2D if dim == 2 else parts[-1].render3D)(tape)
+    nbytes = parts[0].exchange_bytes(dim)
+    assert nbytes == (size // 64) ** 2 // world * 4096 * (6 if dim == 3 else 1)
+    gathered = torch.empty(world * nbytes, dtype=torch.uint8, device="cuda")
+    for r, p in enumerate(parts):
+        p.exchange_pack(dim, gathered.data_ptr() + r * nbytes)
+    torch.cuda.synchronize()
+    for p in parts:
+        p.exchange_unpack(dim, gathered.data_ptr())
+    torch.cuda.synchronize()
+    for p in parts:
+        assert np.array_equal(p.image(), full.image())
+        if dim == 3:
+            assert np.array_equal(p.normals(), full.normals())
+        p.close()
+    assert full.exchange_bytes(dim) == 0             # an unsharded context has nothing to exchange
+    full.close()
+
+
 def test_arena_exhaustion_degrades_like_the_reference():
     """With a tiny arena, tiles keep their parent tape (reference context.cu:336-347); the image
     is still correct because every tape that was kept is valid for its tile."""
