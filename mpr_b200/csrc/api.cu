@@ -319,8 +319,6 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         // Host-buffer entry points pay the upload every frame: host cells -> pinned staging -> HBM.
         if (c->stage_cells_cap < n_chunked) {
             if (c->stage_cells) cudaFreeHost(c->stage_cells);
-    if (c->heat_units) cudaFree(c->heat_units);
-    if (c->owned_tiles) cudaFree(c->owned_tiles);
             c->stage_cells = nullptr;
             MPRB_CUDA(cudaMallocHost(&c->stage_cells, sizeof(uint64_t) * size_t(n_chunked)));
             c->stage_cells_cap = n_chunked;
@@ -675,6 +673,8 @@ void mprb_ctx_destroy(mprb_ctx* c) {
     if (c->ctl) cudaFree(c->ctl);
     if (c->ctl_host) cudaFreeHost(c->ctl_host);
     if (c->stage_cells) cudaFreeHost(c->stage_cells);
+    if (c->heat_units) cudaFree(c->heat_units);
+    if (c->owned_tiles) cudaFree(c->owned_tiles);
     if (c->host_plan) mprb_tape_destroy(c->host_plan);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
