@@ -805,14 +805,24 @@ int mprb_render2d_heatmap(mprb_ctx* c, const mprb_tape* t, const float mat3[9], 
     if (!c || !t || !mat3 || !heatmap) return fail(MPRB_E_ARG, "null argument");
     if (int e = render(c, 2, t, false, mat3, z, true)) return e;
     if (int e = heatmap_out(c, t, heatmap)) return e;
-    return finish(c, 2);
+    const int e = finish(c, 2);
+    if (e) {              // e.g. a tile list overflowed: the caller gets no half-valid buffer to free
+        cudaFree(*heatmap);
+        *heatmap = nullptr;
+    }
+    return e;
 }
 
 int mprb_render3d_heatmap(mprb_ctx* c, const mprb_tape* t, const float mat4[16], float** heatmap) {
     if (!c || !t || !mat4 || !heatmap) return fail(MPRB_E_ARG, "null argument");
     if (int e = render(c, 3, t, false, mat4, 0.0f, true)) return e;
     if (int e = heatmap_out(c, t, heatmap)) return e;
-    return finish(c, 3);
+    const int e = finish(c, 3);
+    if (e) {              // e.g. a tile list overflowed: the caller gets no half-valid buffer to free
+        cudaFree(*heatmap);
+        *heatmap = nullptr;
+    }
+    return e;
 }
 
 int mprb_render2d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
