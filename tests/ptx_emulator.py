@@ -1,0 +1,245 @@
+"""A small interpreter for the PTX subset used by the generated clause-loop handlers
+(tools/gen_interval_loop.py): enough to run a handler's arithmetic on the CPU, one lane at a time,
+with IEEE directed rounding done in exact rational arithmetic.  Test infrastructure only.
+
+Registers hold raw 32-bit patterns; float instructions reinterpret them.  Supported: mov, neg, abs,
+add/sub/mul/div/sqrt with .rm / .rp / .rn, min, max, setp (f32 and u32), selp, and/or/not on
+predicates, and/or/shl/shr/add on b32, mad.wide.u32, predicated st.u32 / mov (the verdict record)."""
+from __future__ import annotations
+
+import math
+import re
+import struct
+from fractions import Fraction
+
+import numpy as np
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def f2b(x) -> int:
+    return struct.unpack("<I", struct.pack("<f", np.float32(x)))[0]
+
+
+def b2f(b: int) -> np.float32:
+    return np.frombuffer(struct.pack("<I", b & 0xffffffff), dtype="<f4")[0]
+
+
+def _round(fr: Fraction, mode: str) -> np.float32:
+    """Exact rational -> float32 under rm (toward -inf), rp (toward +inf) or rn."""
+    if fr == 0:
+        return np.float32(0.0)
+    with np.errstate(over="ignore", under="ignore"):
+        c = np.float32(float(fr)) if abs(fr) < Fraction(10) ** 60 else np.float32(math.copysign(math.inf, fr))
+    if mode == "rn":
+        # float(fr) is correctly rounded to double; double -> float32 can double-round only on exact
+        # ties of the float32 grid, which the callers' operands (float32 sums / products) cannot produce
+        # except through the paths below - resolve by exact comparison of the two neighbours.
+        if math.isinf(c):
+            return c
+        lo = c if Fraction(float(c)) <= fr else np.nextafter(c, np.float32(-np.inf))
+        hi = np.nextafter(lo, np.float32(np.inf))
+        if math.isinf(hi):
+            return lo if fr - Fraction(float(lo)) < Fraction(float(np.finfo(np.float32).max)) * Fraction(1, 2 ** 25) else hi
+        dl, dh = fr - Fraction(float(lo)), Fraction(float(hi)) - fr
+        if dl != dh:
+            return lo if dl < dh else hi
+        return lo if (f2b(lo) & 1) == 0 else hi
+    inf, ninf = np.float32(np.inf), np.float32(-np.inf)
+    if math.isinf(c):
+        c = np.float32(FLT_MAX if c > 0 else -FLT_MAX)
+    with np.errstate(over="ignore"):
+        lo = c
+        while not math.isinf(lo) and Fraction(float(lo)) > fr:        # step down to a float32 <= fr
+            lo = np.nextafter(lo, ninf)
+        if math.isinf(lo):                                            # fr < -FLT_MAX
+            return ninf if mode == "rm" else np.float32(-FLT_MAX)
+        while True:                                                   # climb to the last float32 <= fr
+            n = np.nextafter(lo, inf)
+            if math.isinf(n) or Fraction(float(n)) > fr:
+                break
+            lo = n
+        if mode == "rm" or Fraction(float(lo)) == fr:
+            return lo
+        return np.nextafter(lo, inf)                                  # +inf beyond FLT_MAX
+
+
+def _zero(sign_negative: bool) -> np.float32:
+    return np.float32(-0.0) if sign_negative else np.float32(0.0)
+
+
+def fadd(a, b, mode):
+    a, b = np.float32(a), np.float32(b)
+    if np.isnan(a) or np.isnan(b):
+        return np.float32(np.nan)
+    if np.isinf(a) or np.isinf(b):
+        if np.isinf(a) and np.isinf(b) and a != b:
+            return np.float32(np.nan)
+        return a if np.isinf(a) else b
+    s = Fraction(float(a)) + Fraction(float(b))
+    if s == 0:
+        if a == 0 and b == 0 and np.signbit(a) == np.signbit(b):
+            return a
+        return _zero(mode == "rm")
+    return _round(s, mode)
+
+
+def fmul(a, b, mode):
+    a, b = np.float32(a), np.float32(b)
+    if np.isnan(a) or np.isnan(b):
+        return np.float32(np.nan)
+    neg = bool(np.signbit(a)) != bool(np.signbit(b))
+    if np.isinf(a) or np.isinf(b):
+        if a == 0 or b == 0:
+            return np.float32(np.nan)
+        return np.float32(-np.inf if neg else np.inf)
+    if a == 0 or b == 0:
+        return _zero(neg)
+    r = _round(Fraction(float(a)) * Fraction(float(b)), mode)
+    return _zero(neg) if r == 0 else r
+
+
+def fdiv(a, b, mode):
+    a, b = np.float32(a), np.float32(b)
+    if np.isnan(a) or np.isnan(b):
+        return np.float32(np.nan)
+    neg = bool(np.signbit(a)) != bool(np.signbit(b))
+    if np.isinf(a):
+        return np.float32(np.nan) if np.isinf(b) else np.float32(-np.inf if neg else np.inf)
+    if np.isinf(b):
+        return _zero(neg)
+    if b == 0:
+        return np.float32(np.nan) if a == 0 else np.float32(-np.inf if neg else np.inf)
+    if a == 0:
+        return _zero(neg)
+    r = _round(Fraction(float(a)) / Fraction(float(b)), mode)
+    return _zero(neg) if r == 0 else r
+
+
+def fsqrt(a, mode):
+    a = np.float32(a)
+    if np.isnan(a) or a < 0:
+        return np.float32(np.nan)
+    if a == 0 or np.isinf(a):
+        return a
+    x = Fraction(float(a))
+    c = np.float32(math.sqrt(float(a)))
+    while Fraction(float(c)) ** 2 > x:
+        c = np.nextafter(c, np.float32(-np.inf))
+    while Fraction(float(np.nextafter(c, np.float32(np.inf)))) ** 2 <= x:
+        c = np.nextafter(c, np.float32(np.inf))
+    if Fraction(float(c)) ** 2 == x or mode == "rm":
+        return c
+    if mode == "rp":
+        return np.nextafter(c, np.float32(np.inf))
+    n = np.nextafter(c, np.float32(np.inf))
+    mid = (Fraction(float(c)) + Fraction(float(n))) / 2
+    return c if mid * mid > x else n
+
+
+def fmin(a, b):
+    a, b = np.float32(a), np.float32(b)
+    if np.isnan(a):
+        return b
+    if np.isnan(b):
+        return a
+    return a if a < b or (a == b and np.signbit(a)) else b
+
+
+def fmax(a, b):
+    a, b = np.float32(a), np.float32(b)
+    if np.isnan(a):
+        return b
+    if np.isnan(b):
+        return a
+    return a if a > b or (a == b and not np.signbit(a)) else b
+
+
+class Machine:
+    def __init__(self, regs=None, operands=None):
+        self.r = dict(regs or {})       # name -> uint32 pattern (or bool for predicates, int for b64)
+        self.ops = dict(operands or {})  # "%3" -> name of the register that stands for it
+        self.stores = []                # (address, value) of st.u32
+
+    def val(self, tok):
+        tok = tok.strip()
+        if tok in self.ops:
+            tok = self.ops[tok]
+        if tok.startswith("0f"):
+            return int(tok[2:], 16)
+        if re.fullmatch(r"-?\d+", tok):
+            return int(tok) & 0xffffffff
+        if re.fullmatch(r"0x[0-9a-fA-F]+", tok):
+            return int(tok, 16)
+        return self.r[tok]
+
+    def set(self, tok, v):
+        tok = tok.strip()
+        self.r[self.ops.get(tok, tok)] = v
+
+    def run(self, text: str):
+        for ins in [i.strip() for i in text.split(";") if i.strip()]:
+            pred = None
+            m = re.match(r"@(!?)(\w+)\s+(.*)", ins)
+            if m:
+                pred = bool(self.r[m.group(2)]) != bool(m.group(1))
+                ins = m.group(3)
+                if not pred:
+                    continue
+            op, rest = ins.split(None, 1)
+            a = [x.strip() for x in rest.replace("[", "").replace("]", "").split(",")]
+            f = lambda k: b2f(self.val(a[k]))
+            if op in ("mov.b32", "mov.f32", "mov.u32"):
+                self.set(a[0], self.val(a[1]))
+            elif op == "neg.f32":
+                self.set(a[0], self.val(a[1]) ^ 0x80000000)
+            elif op == "abs.f32":
+                self.set(a[0], self.val(a[1]) & 0x7fffffff)
+            elif re.fullmatch(r"(add|sub|mul|div)\.(rm|rp|rn)\.f32", op):
+                kind, mode, _ = op.split(".")
+                x, y = f(1), f(2)
+                if kind == "sub":
+                    y = np.float32(-y) if not np.isnan(y) else y
+                fn = {"add": fadd, "sub": fadd, "mul": fmul, "div": fdiv}[kind]
+                self.set(a[0], f2b(fn(x, y, mode)))
+            elif re.fullmatch(r"sqrt\.(rm|rp|rn)\.f32", op):
+                self.set(a[0], f2b(fsqrt(f(1), op.split(".")[1])))
+            elif op == "min.f32":
+                self.set(a[0], f2b(fmin(f(1), f(2))))
+            elif op == "max.f32":
+                self.set(a[0], f2b(fmax(f(1), f(2))))
+            elif re.fullmatch(r"setp\.(lt|gt|le|ge|eq|ne)\.f32", op):
+                x, y = f(1), f(2)
+                c = op.split(".")[1]
+                self.set(a[0], bool({"lt": x < y, "gt": x > y, "le": x <= y, "ge": x >= y, "eq": x == y, "ne": x != y}[c]))
+            elif re.fullmatch(r"setp\.(lt|gt|le|ge|eq|ne)\.u32", op):
+                x, y = self.val(a[1]), self.val(a[2])
+                c = op.split(".")[1]
+                self.set(a[0], {"lt": x < y, "gt": x > y, "le": x <= y, "ge": x >= y, "eq": x == y, "ne": x != y}[c])
+            elif op == "selp.b32":
+                self.set(a[0], self.val(a[1]) if self.r[a[3]] else self.val(a[2]))
+            elif op == "and.pred":
+                self.set(a[0], bool(self.r[a[1]]) and bool(self.r[a[2]]))
+            elif op == "or.pred":
+                self.set(a[0], bool(self.r[a[1]]) or bool(self.r[a[2]]))
+            elif op == "not.pred":
+                self.set(a[0], not bool(self.r[a[1]]))
+            elif op == "and.b32":
+                self.set(a[0], self.val(a[1]) & self.val(a[2]))
+            elif op == "or.b32":
+                self.set(a[0], self.val(a[1]) | self.val(a[2]))
+            elif op == "shl.b32":
+                s = self.val(a[2])
+                self.set(a[0], (self.val(a[1]) << s) & 0xffffffff if s < 32 else 0)
+            elif op == "shr.u32":
+                s = self.val(a[2])
+                self.set(a[0], self.val(a[1]) >> s if s < 32 else 0)
+            elif op == "add.u32":
+                self.set(a[0], (self.val(a[1]) + self.val(a[2])) & 0xffffffff)
+            elif op == "mad.wide.u32":
+                self.set(a[0], self.val(a[1]) * self.val(a[2]) + self.val(a[3]))
+            elif op == "st.u32":
+                self.stores.append((self.val(a[0]), self.val(a[1])))
+            else:
+                raise NotImplementedError(ins)
+        return self

@@ -234,3 +234,75 @@ def test_interval_multiply_operand_selection_matches_the_nine_case_table():
         s = mod.mul_select(bool(ca & 1), bool(ca & 2), bool(cb & 1), bool(cb & 2))
         got = ("ah" if s[0] else "al", "bl" if s[1] else "bh", "al" if s[2] else "ah", "bl" if s[3] else "bh")
         assert got == want, (ca, cb)
+
+
+# ---- the generated interval handlers, executed on the CPU -------------------------------------
+
+def _interval_handler(op):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_interval_loop", ROOT / "tools" / "gen_interval_loop.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return " ".join(mod.compute(op))
+
+
+_IV_OPS = {"SQUARE": 2, "SQRT": 3, "NEG": 4, "SIN": 5, "ABS": 11, "ADD_LI": 13, "ADD_LR": 14, "MUL_LI": 15, "MUL_LR": 16,
+           "MIN_LI": 17, "MIN_LR": 18, "MAX_LI": 19, "MAX_LR": 20, "SUB_LI": 21, "SUB_IR": 22, "SUB_LR": 23, "DIV_LI": 24}
+
+
+@pytest.mark.parametrize("name", sorted(_IV_OPS))
+def test_generated_interval_handlers_equal_the_c_restatement(name):
+    """Runs the PTX text of each interval handler (tools/gen_interval_loop.py) through a small
+    interpreter with exact directed rounding (tests/ptx_emulator.py) and compares bounds and min/max
+    verdicts with oracle/mpr_oracle.c, on ordinary intervals and on the awkward ones: zero-width,
+    zero-straddling, infinite, inverted and NaN bounds."""
+    import oracle
+    from ptx_emulator import Machine, b2f, f2b
+    L = oracle.oracle_lib()
+    L.mpro_interval_op.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    op = _IV_OPS[name]
+    text = _interval_handler(op)
+    rng = np.random.default_rng(op)
+    special = [0.0, -0.0, 1.0, -1.0, 0.5, -2.5, 3.0, 1e-30, -1e-30, 1e30, -1e30, np.inf, -np.inf, np.nan,
+               float(np.finfo(np.float32).max), float(np.finfo(np.float32).tiny), 1e-45]
+    cases = []
+    for _ in range(120):
+        a = np.sort(rng.normal(0, 2, 2)).astype(np.float32)
+        b = np.sort(rng.normal(0, 2, 2)).astype(np.float32)
+        cases.append((a, b))
+    for _ in range(120):
+        a = np.array(rng.choice(special, 2), dtype=np.float32)
+        b = np.array(rng.choice(special, 2), dtype=np.float32)
+        cases.append((a, b))
+    swap_r = name in ("SUB_IR",)            # the oracle hook takes the interval operand first
+    for a, b in cases:
+        imm = np.float32(b[0])
+        regs = {"ll": f2b(a[0]), "lh": f2b(a[1]), "rl": f2b(b[0]), "rh": f2b(b[1]), "im": f2b(imm),
+                "cw": 0, "n": 5, "any": 0, "chbase": 0}
+        if swap_r:
+            regs.update(rl=f2b(a[0]), rh=f2b(a[1]))
+        m = Machine(regs, {"%3": "cw", "%4": "n", "%5": "any", "%7": "chbase"}).run(text)
+        got = np.array([b2f(m.r["ol"]), b2f(m.r["oh"])], dtype=np.float32)
+        want = np.zeros(2, dtype=np.float32)
+        fa = np.ascontiguousarray(a)
+        fb = np.ascontiguousarray(b)
+        ch = L.mpro_interval_op(op, fa.ctypes.data, fb.ctypes.data, want.ctypes.data)
+        same = (got == want) | (np.isnan(got) & np.isnan(want))
+        assert same.all(), (name, a, b, got, want)
+        if 17 <= op <= 20:
+            assert m.r["c"] == ch, (name, a, b, m.r["c"], ch)
+            # verdict record: bits (n & 15) * 2 of cw, counter advanced, flag raised iff decided
+            assert m.r["cw"] == (ch << 10) and m.r["n"] == 6 and (m.r["any"] != 0) == (ch != 0)
+            assert not m.stores
+
+
+def test_generated_verdict_record_flushes_every_sixteenth_verdict():
+    from ptx_emulator import Machine, f2b
+    text = _interval_handler(18)            # MIN_LHS_RHS
+    base = {"ll": f2b(0.0), "lh": f2b(1.0), "rl": f2b(2.0), "rh": f2b(3.0), "im": 0, "chbase": 1000}
+    # 16th verdict of a word (n = 31): the word goes to choices[1] and restarts
+    m = Machine(dict(base, cw=0x12345, n=31, any=0), {"%3": "cw", "%4": "n", "%5": "any", "%7": "chbase"}).run(text)
+    assert m.r["c"] == 1 and m.stores == [(1000 + 4 * 1, 0x12345 | (1 << 30))] and m.r["cw"] == 0 and m.r["n"] == 32
+    # past the 4096-verdict record nothing is stored, the word still restarts (context.cu:257-259)
+    m = Machine(dict(base, cw=7, n=4111, any=0), {"%3": "cw", "%4": "n", "%5": "any", "%7": "chbase"}).run(text)
+    assert m.stores == [] and m.r["cw"] == 0 and m.r["n"] == 4112 and m.r["any"] == 1
