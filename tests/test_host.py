@@ -306,3 +306,72 @@ def test_generated_verdict_record_flushes_every_sixteenth_verdict():
     # past the 4096-verdict record nothing is stored, the word still restarts (context.cu:257-259)
     m = Machine(dict(base, cw=7, n=4111, any=0), {"%3": "cw", "%4": "n", "%5": "any", "%7": "chbase"}).run(text)
     assert m.stores == [] and m.r["cw"] == 0 and m.r["n"] == 4112 and m.r["any"] == 1
+
+
+@pytest.mark.parametrize("tool", ["gen_float_loop", "gen_interval_loop"])
+def test_forwarding_hints_preserve_the_slot_state_on_random_tapes(tool):
+    """Model check of the hint scheme the PTX loops rely on (kernels.cu:annotate_chunk +
+    tools/gen_*_loop.py): FL / FR take an operand from the previous result instead of its slot, NS
+    skips a store the next clause overwrites.  On random chunks - slot ids colliding on purpose,
+    operands equal to the destination, slow cells and jumps in between - running with the hints must
+    leave exactly the slot values of plain sequential execution at every point where the loop hands
+    control back (those are the only points where anything else reads the slots)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(tool, ROOT / "tools" / f"{tool}.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    fast_ops, uses_l, uses_r = sorted(mod.OPS), mod.USES_L, mod.USES_R
+    slow_ops = [o for o in range(2, 30) if o not in mod.OPS] + [0, 1]
+    P = (1 << 61) - 1
+
+    def apply(op, l, r, imm):                      # an arbitrary non-commutative stand-in for the arithmetic
+        l = l if op in uses_l else 0
+        r = r if op in uses_r else 0
+        return (op * 1000003 + l * 7919 + r * 104729 + imm * 31 + 17) % P
+
+    def annotate(cells):                            # mirrors annotate_chunk<FAST, LHS, RHS>
+        fast = lambda c: c is not None and c["op"] in mod.OPS
+        out = []
+        for j, c in enumerate(cells):
+            prev = cells[j - 1] if j > 0 else None
+            nxt = cells[j + 1] if j + 1 < len(cells) else None
+            fl = fr = ns = False
+            if fast(c):
+                if fast(prev):
+                    fl = c["op"] in uses_l and c["lhs"] == prev["out"]
+                    fr = c["op"] in uses_r and c["rhs"] == prev["out"]
+                ns = fast(nxt) and nxt["out"] == c["out"]
+            out.append((fl, fr, ns))
+        return out
+
+    rng = np.random.default_rng(7)
+    for trial in range(300):
+        n = 64
+        cells = []
+        for j in range(n):
+            op = int(rng.choice(fast_ops)) if rng.random() < 0.85 else int(rng.choice(slow_ops))
+            cells.append(dict(op=op, out=int(rng.integers(1, 6)), lhs=int(rng.integers(0, 6)), rhs=int(rng.integers(0, 6)),
+                              imm=int(rng.integers(0, 100))))
+        hints = annotate(cells)
+        plain = {s: 1000 + s for s in range(6)}
+        smem = dict(plain)
+        reg = None                                  # (ox, oy) of the PTX loop
+        for j, c in enumerate(cells):
+            if c["op"] not in mod.OPS:              # the loop exits here: slots must agree
+                assert smem == plain, (tool, trial, j)
+                reg = None
+                if c["op"] >= 2:                    # a slow clause runs in C++ on the slots
+                    v = apply(c["op"], plain[c["lhs"]], plain[c["rhs"]], c["imm"])
+                    plain[c["out"]] = smem[c["out"]] = v
+                continue
+            fl, fr, ns = hints[j]
+            want = apply(c["op"], plain[c["lhs"]], plain[c["rhs"]], c["imm"])
+            plain[c["out"]] = want
+            assert not (fl or fr) or reg is not None
+            l = reg if fl else smem[c["lhs"]]
+            r = reg if fr else smem[c["rhs"]]
+            got = apply(c["op"], l, r, c["imm"])
+            assert got == want, (tool, trial, j, c, hints[j])
+            if not ns:
+                smem[c["out"]] = got
+            reg = got
