@@ -6,7 +6,7 @@ NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Impr_b200/shim -
 CXXFLAGS  := -O2 -std=c++17 -fPIC -Impr_b200/shim -Impr_b200/inc -Impr_b200/csrc/host
 BUILD     := build
 
-CU_SRCS   := mpr_b200/csrc/kernels.cu mpr_b200/csrc/effects.cu mpr_b200/csrc/api.cu
+CU_SRCS   := mpr_b200/csrc/kernels.cu mpr_b200/csrc/postfx.cu mpr_b200/csrc/exchange.cu mpr_b200/csrc/api.cu
 CXX_SRCS  := mpr_b200/csrc/host/tree.cpp mpr_b200/csrc/host/tape_build.cpp mpr_b200/csrc/host/cxx_api.cpp
 OBJS      := $(patsubst %.cu,$(BUILD)/%.o,$(CU_SRCS)) $(patsubst %.cpp,$(BUILD)/%.o,$(CXX_SRCS))
 
@@ -21,7 +21,7 @@ $(BUILD)/%.o: %.cu $(wildcard mpr_b200/csrc/*.cuh) $(wildcard mpr_b200/csrc/*.in
 
 # The post-effect kernels are compiled without FMA contraction so that they can be compared
 # cell for cell with the CPU restatement (oracle/mpr_oracle.c, built with -ffp-contract=off).
-$(BUILD)/mpr_b200/csrc/effects.o: NVFLAGS += -fmad=false
+$(BUILD)/mpr_b200/csrc/postfx.o: NVFLAGS += -fmad=false
 
 $(BUILD)/%.o: %.cpp
 	@mkdir -p $(dir $@)

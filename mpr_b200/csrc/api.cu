@@ -24,7 +24,8 @@
 #include "../../include/mprb.h"
 #include "common.cuh"
 #include "host/mprb_host.hpp"
-#include "effects.cuh"
+#include "exchange.cuh"
+#include "postfx.cuh"
 #include "kernels.cuh"
 #include "libfive/tree/archive.hpp"
 

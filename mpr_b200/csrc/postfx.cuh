@@ -1,4 +1,4 @@
-// Launchers of the post-effect kernels (effects.cu).
+// Launchers of the post-effect kernels (postfx.cu).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -9,8 +9,4 @@ void launch_draw_ssao(const int32_t* depth, const uint32_t* norm, const float* k
 void launch_blur_ssao(const int32_t* image, const int32_t* ssao, int size, int32_t* out, cudaStream_t s);
 void launch_draw_shaded(const int32_t* depth, const uint32_t* norm, const int32_t* ssao, int size, int32_t* out,
                         cudaStream_t s);
-// Multi-GPU exchange (effects.cu): bytes one rank contributes, and the pack / unpack launches.
-size_t exchange_rank_bytes(int size, int world, int dim);
-void launch_exchange(bool pack, int size, int world, int rank, int col_step, int dim, int32_t* depth, uint32_t* normals,
-                     void* buf, cudaStream_t s);
 }  // namespace mprb
