@@ -136,6 +136,10 @@ struct TapeStream {
     }
 
     __device__ __forceinline__ void load_chunk(int want) {
+        // Without renaming the walkers annotate the raw chunk in place (generic-proxy byte stores,
+        // kernels.cu:annotate_chunk); the bulk copy below writes the same bytes through the async
+        // proxy, so those stores are ordered before it explicitly.
+        if (!REMAP) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();                                   // everyone is done reading the old chunk
         if ((threadIdx.x & 31) == 0) {
             const uint64_t* src = arena + want;
