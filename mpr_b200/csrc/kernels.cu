@@ -18,6 +18,14 @@
 //   k_eval_voxels             3D float pass: a warp owns one 4x4x4 tile, two voxels per lane
 //   k_eval_root<DIM>          root level, clause-parallel over an SSA / levelised root tape
 //   k_normals                 per-pixel gradient pass, lanes grouped by tape
+//   k_preload_tiles, k_heat_finish   brute-force frames and the work meter (analysis variants)
+//
+// Without slot renaming (<= 32 slot ids) the clause loops of the interval and float passes are
+// generated PTX (interval_loop_ptx.inc, float_loop_ptx.inc; tools/gen_*_loop.py): one indexed
+// branch per clause, operand forwarding and dead-store elision driven by hint bits that
+// annotate_chunk() writes into the spare bits of the opcode byte when a chunk lands in shared
+// memory.  HEAT = true instantiations are the work-metering variants; ordinary frames never run
+// them.
 //
 // Behaviour (what is computed, bit for bit) follows the reference kernels in
 // reference src/context.cu; line numbers are cited at each step.  How it is
