@@ -243,3 +243,74 @@ class Machine:
             else:
                 raise NotImplementedError(ins)
         return self
+
+
+# ---- whole-loop execution: labels, the branch table, shared memory ---------------------------------
+
+def load_asm(path) -> str:
+    """The asm template of a generated *_ptx.inc as one string, local-label suffixes removed."""
+    text = "".join(re.findall(r'"((?:[^"\\]|\\.)*)"', open(path).read()))
+    return text.replace("\\n", "\n").replace("_%=", "")
+
+
+class LoopMachine(Machine):
+    """Runs a complete generated clause loop for ONE lane: `smem` maps 4-byte-aligned shared
+    addresses to 32-bit words; operands %0.. are bound to registers by name."""
+
+    def __init__(self, asm: str, regs, operands, smem):
+        super().__init__(regs, operands)
+        self.smem = smem
+        body = asm[asm.index("{") + 1: asm.rindex("}")]
+        m = re.search(r"(\w+):\s*\.branchtargets([^;]*);", body)
+        self.table = [t.strip() for t in m.group(2).replace("\n", " ").split(",")]
+        body = body[:m.start()] + body[m.end():]
+        self.prog, self.labels = [], {}
+        for stmt in body.split(";"):
+            stmt = stmt.strip()
+            while True:
+                lm = re.match(r"(\w+):\s*(.*)", stmt, re.S)
+                if not lm:
+                    break
+                self.labels[lm.group(1)] = len(self.prog)
+                stmt = lm.group(2).strip()
+            if stmt and not stmt.startswith(".reg"):
+                self.prog.append(stmt)
+
+    def execute(self, max_steps=200000):
+        pc = 0
+        for _ in range(max_steps):
+            if pc >= len(self.prog):
+                return self
+            ins = self.prog[pc]
+            pc += 1
+            pm = re.match(r"@(!?)(\w+)\s+(.*)", ins, re.S)
+            if pm:
+                if bool(self.r[pm.group(2)]) == bool(pm.group(1)):
+                    continue
+                ins = pm.group(3)
+            op = ins.split(None, 1)[0]
+            if op == "bra.uni":
+                pc = self.labels[ins.split()[1]]
+            elif op == "brx.idx.uni":
+                idx = self.val(ins.split(None, 1)[1].split(",")[0])
+                pc = self.labels[self.table[idx]]
+            elif op == "ld.shared.v2.b32":
+                m = re.match(r"ld\.shared\.v2\.b32\s*\{(.+?),(.+?)\}\s*,\s*\[(.+?)\]", ins)
+                addr = self.val(m.group(3))
+                self.set(m.group(1), self.smem.get(addr, 0))
+                self.set(m.group(2), self.smem.get(addr + 4, 0))
+            elif op == "st.shared.v2.b32":
+                m = re.match(r"st\.shared\.v2\.b32\s*\[(.+?)\]\s*,\s*\{(.+?),(.+?)\}", ins)
+                addr = self.val(m.group(1))
+                self.smem[addr] = self.val(m.group(2))
+                self.smem[addr + 4] = self.val(m.group(3))
+            elif op == "prmt.b32":
+                a = [x.strip() for x in ins.split(None, 1)[1].split(",")]
+                src = (self.val(a[2]) << 32) | self.val(a[1])
+                sel, out = self.val(a[3]), 0
+                for k in range(4):
+                    out |= ((src >> (8 * ((sel >> (4 * k)) & 7))) & 0xff) << (8 * k)
+                self.set(a[0], out)
+            else:
+                self.run(ins)
+        raise RuntimeError("loop did not finish")

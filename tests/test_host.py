@@ -375,3 +375,145 @@ def test_forwarding_hints_preserve_the_slot_state_on_random_tapes(tool):
             if not ns:
                 smem[c["out"]] = got
             reg = got
+
+
+def _mini_annotate(cells, mod):
+    """annotate_chunk (kernels.cu) on a list of raw 64-bit cells; returns cells with hint bits."""
+    fast = lambda c: c is not None and (c & 0xff) in mod.OPS
+    out = []
+    for j, c in enumerate(cells):
+        prev = cells[j - 1] if j > 0 else None
+        nxt = cells[j + 1] if j + 1 < len(cells) else None
+        flags = 0
+        if fast(c):
+            op = c & 0xff
+            if fast(prev):
+                if op in mod.USES_L and ((c >> 16) & 0xff) == ((prev >> 8) & 0xff):
+                    flags |= 0x20
+                if op in mod.USES_R and ((c >> 24) & 0xff) == ((prev >> 8) & 0xff):
+                    flags |= 0x40
+            if fast(nxt) and ((nxt >> 8) & 0xff) == ((c >> 8) & 0xff):
+                flags |= 0x80
+        out.append(c | flags)
+    return out
+
+
+def test_generated_interval_loop_runs_whole_tapes_like_the_c_restatement():
+    """The complete generated interval loop - table dispatch, byte-permute addressing, hinted
+    handler variants, stores, verdict record - executed on the CPU for one lane over random
+    annotated tapes, against clause-by-clause evaluation with oracle/mpr_oracle.c."""
+    import importlib.util
+    import oracle
+    from ptx_emulator import LoopMachine, b2f, f2b, load_asm
+    spec = importlib.util.spec_from_file_location("gen_interval_loop", ROOT / "tools" / "gen_interval_loop.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    asm = load_asm(ROOT / "mpr_b200" / "csrc" / "interval_loop_ptx.inc")
+    L = oracle.oracle_lib()
+    L.mpro_interval_op.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    ops = [o for o in sorted(mod.OPS) if o != 10]          # exp uses ex2.approx: not emulated
+    rng = np.random.default_rng(11)
+    CH, SB, CHOICES = 0x1000, 0x4000, 0x100000
+    for trial in range(40):
+        n = int(rng.integers(5, 40))
+        cells = []
+        for _ in range(n):
+            op = int(rng.choice(ops))
+            imm = np.float32(rng.choice([0.0, 1.5, -2.0, 0.25, -0.75, 3.0]))
+            cells.append(op | int(rng.integers(1, 7)) << 8 | int(rng.integers(0, 7)) << 16 | int(rng.integers(0, 7)) << 24
+                         | f2b(imm) << 32)
+        cells.append(0 | (int(rng.integers(1, 7)) << 8))            # END cell
+        noted = _mini_annotate(cells, mod)
+        smem = {}
+        for j, c in enumerate(noted):
+            smem[CH + 8 * j], smem[CH + 8 * j + 4] = c & 0xffffffff, c >> 32
+        slots = {s: np.sort(rng.normal(0, 2, 2)).astype(np.float32) for s in range(7)}
+        for s, v in slots.items():
+            smem[SB + 256 * s], smem[SB + 256 * s + 4] = f2b(v[0]), f2b(v[1])
+        m = LoopMachine(asm, {"cp": CH - 8, "sb": SB, "cw": 0, "n": 3, "any": 0, "ch": CHOICES, "w": 0, "imm": 0},
+                        {"%0": "cp", "%1": "w", "%2": "imm", "%3": "cw", "%4": "n", "%5": "any", "%6": "sb", "%7": "ch"},
+                        smem).execute()
+        assert m.r["cp"] == CH + 8 * n and (m.r["w"] & 0xff) == 0       # stopped on the END cell
+        # clause-by-clause reference
+        cw, cnt, anyc = 0, 3, 0
+        for c in cells[:-1]:
+            op, out, lhs, rhs = c & 0xff, (c >> 8) & 0xff, (c >> 16) & 0xff, (c >> 24) & 0xff
+            imm = np.array([b2f(c >> 32), 0], dtype=np.float32)
+            a = slots[lhs].copy()
+            b = slots[rhs].copy()
+            if op in (22,):                                 # SUB_IMM_RHS: the hook takes the interval first
+                a = b
+            second = imm if op in (13, 15, 17, 19, 21, 22, 24, 27) else b
+            res = np.zeros(2, dtype=np.float32)
+            if op == 27:
+                res[:] = imm[0]
+                ch = 0
+            elif op == 28:
+                res, ch = slots[lhs].copy(), 0
+            elif op == 29:
+                res, ch = slots[rhs].copy(), 0
+            else:
+                ch = L.mpro_interval_op(op, a.ctypes.data, np.ascontiguousarray(second).ctypes.data, res.ctypes.data)
+            if 17 <= op <= 20:
+                cw |= ch << ((cnt & 15) * 2)
+                if (cnt & 15) == 15:
+                    cw = 0
+                cnt += 1
+                anyc |= ch
+            slots[out] = res
+        for s, v in slots.items():
+            got = np.array([b2f(smem[SB + 256 * s]), b2f(smem[SB + 256 * s + 4])], dtype=np.float32)
+            assert ((got == v) | (np.isnan(got) & np.isnan(v))).all(), (trial, s, got, v)
+        assert (m.r["cw"], m.r["n"], m.r["any"] != 0) == (cw, cnt, anyc != 0)
+
+
+def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation():
+    """Same for the float pass's loop (two samples per lane), against numpy float32 arithmetic with the
+    clause semantics of eval_voxels_f (reference context.cu:887-920).  exp / log are left out: their
+    handlers are libdevice's PTX (ex2.approx), which the interpreter does not model."""
+    import importlib.util
+    from ptx_emulator import LoopMachine, b2f, f2b, fmax, fmin, load_asm
+    spec = importlib.util.spec_from_file_location("gen_float_loop", ROOT / "tools" / "gen_float_loop.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    asm = load_asm(ROOT / "mpr_b200" / "csrc" / "float_loop_ptx.inc")
+    ops = [o for o in sorted(mod.OPS) if o not in (10, 12)]
+    rng = np.random.default_rng(5)
+    CH, SB = 0x1000, 0x4000
+    f32 = np.float32
+
+    def clause(op, l, r, imm):
+        with np.errstate(all="ignore"):
+            return {2: lambda: l * l, 3: lambda: np.sqrt(l), 4: lambda: -l, 11: lambda: np.abs(l),
+                    13: lambda: l + imm, 14: lambda: l + r, 15: lambda: l * imm, 16: lambda: l * r,
+                    17: lambda: fmin(l, imm), 18: lambda: fmin(l, r), 19: lambda: fmax(l, imm), 20: lambda: fmax(l, r),
+                    21: lambda: l - imm, 22: lambda: imm - r, 23: lambda: l - r,
+                    24: lambda: l / imm, 25: lambda: imm / r, 26: lambda: l / r,
+                    27: lambda: imm, 28: lambda: l, 29: lambda: r}[op]()
+
+    for trial in range(40):
+        n = int(rng.integers(5, 40))
+        cells = []
+        for _ in range(n):
+            op = int(rng.choice(ops))
+            imm = f32(rng.choice([0.0, 1.5, -2.0, 0.25, -0.75, 3.0]))
+            cells.append(op | int(rng.integers(1, 7)) << 8 | int(rng.integers(0, 7)) << 16 | int(rng.integers(0, 7)) << 24
+                         | f2b(imm) << 32)
+        cells.append(0 | (int(rng.integers(1, 7)) << 8))
+        noted = _mini_annotate(cells, mod)
+        smem = {}
+        for j, c in enumerate(noted):
+            smem[CH + 8 * j], smem[CH + 8 * j + 4] = c & 0xffffffff, c >> 32
+        slots = {s: rng.normal(0, 2, 2).astype(f32) for s in range(7)}
+        for s, v in slots.items():
+            smem[SB + 256 * s], smem[SB + 256 * s + 4] = f2b(v[0]), f2b(v[1])
+        m = LoopMachine(asm, {"cp": CH - 8, "sb": SB, "w": 0, "imm": 0},
+                        {"%0": "cp", "%1": "w", "%2": "imm", "%3": "sb"}, smem).execute()
+        assert m.r["cp"] == CH + 8 * n and (m.r["w"] & 0xff) == 0
+        for c in cells[:-1]:
+            op, out, lhs, rhs = c & 0xff, (c >> 8) & 0xff, (c >> 16) & 0xff, (c >> 24) & 0xff
+            imm = b2f(c >> 32)
+            slots[out] = np.array([clause(op, slots[lhs][k], slots[rhs][k], imm) for k in range(2)], dtype=f32)
+        for s, v in slots.items():
+            got = np.array([b2f(smem[SB + 256 * s]), b2f(smem[SB + 256 * s + 4])], dtype=f32)
+            assert ((got == v) | (np.isnan(got) & np.isnan(v))).all(), (trial, s, got, v)
