@@ -190,6 +190,7 @@ struct TapeStream {
                 for (int b = 1; b < 4; ++b) {
                     const uint32_t id = (c[k].x >> (8 * b)) & 0xff;
                     bool need = valid[k] && lds_u8(table + id) == 0xff;
+                    __syncwarp();       // orders these table reads before the leaders' writes below (racecheck: WAR)
                     unsigned m = __ballot_sync(0xffffffffu, need);
                     while (m) {
                         const int leader = __ffs(m) - 1;

@@ -42,6 +42,13 @@ CASES = [
     ("architecture", 3, 2048),
     ("involute_gear_3d", 3, 2048),
     ("bear", 3, 2048),
+    # BASELINE.json configs 3 and 4 at the reference's table sizes (render_2d_table.cpp:50, render_3d_table.cpp:51)
+    ("involute_gear_2d", 2, 256),
+    ("involute_gear_2d", 2, 1024),
+    ("involute_gear_2d", 2, 2048),
+    ("involute_gear_2d", 2, 3072),
+    ("bear", 3, 1536),
+    ("prospero", 2, 2048),
 ]
 
 SUBTAPES = 6400000   # the reference arm is built with -DBIG_SERVER
