@@ -19,9 +19,6 @@ $(BUILD)/%.o: %.cu $(wildcard mpr_b200/csrc/*.cuh) $(wildcard mpr_b200/csrc/*.in
 	@mkdir -p $(dir $@)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-# The post-effect kernels are compiled without FMA contraction so that they can be compared
-# cell for cell with the CPU restatement (oracle/mpr_oracle.c, built with -ffp-contract=off).
-$(BUILD)/mpr_b200/csrc/postfx.o: NVFLAGS += -fmad=false
 
 $(BUILD)/%.o: %.cpp
 	@mkdir -p $(dir $@)

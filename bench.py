@@ -39,8 +39,17 @@ PEAKS = ROOT / "MEASURED_PEAKS.json"
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+# The reference's table protocol (benchmark/render_2d_table.cpp:50, render_3d_table.cpp:51, run_benchmarks.sh:24-56):
+# every size of the 2D table on prospero, every size of the 3D table on bear that its arena can hold
+# (bear 2048^3 overflows the reference's subtape arena and is nondeterministic there).
+SWEEP = ",".join([f"prospero_2d_{s}" for s in (256, 512, 1024, 2048, 3072, 4096)] +
+                 [f"bear_3d_{s}" for s in (256, 512, 1024, 1536)])
+
+
 def parse_workloads(spec: str):
     out = []
+    if spec == "sweep":
+        spec = SWEEP
     for w in spec.split(","):
         model, dim, size = w.rsplit("_", 2)
         out.append((model, int(dim[0]), int(size)))
@@ -94,11 +103,38 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(workloads, budget_s: float = 60.0) -> dict:
-    """The CPU restatement (oracle/mpr_oracle.c) on all host cores: one frame per workload."""
+def cpu_baseline(workloads, budget_s: float = 45.0) -> dict:
+    """Two CPU arms on the host cores, each on a bounded sample of the same workload:
+      * `value`: libfive's CPU renderer as the reference drivers call it (Heightmap::render,
+        libfive/src/render/discrete/heightmap.cpp:195-318) - libfive itself cannot be built here (Eigen, Boost,
+        libpng absent), so this is the stand-in the unchanged reference drivers link
+        (mpr_b200/shim/src/heightmap_render.cpp: interval region recursion + point samples, no tape
+        shortening) behind oracle/heightmap_cabi.cpp, fed the expression rebuilt from the packed tape;
+      * `gpu_algorithm_port`: oracle/mpr_oracle.c, the tile-recursive GPU algorithm on OpenMP threads."""
     import oracle
-    t_total, frames, sample = 0.0, 0, []
     threads = oracle.oracle_lib().mpro_max_threads()
+    out = {"unit": "ms/frame", "cores": threads, "kind": "port"}
+    # (a) libfive-algorithm stand-in, at a resolution it finishes in seconds, scaled to the workload's
+    t_total, frames, sample = 0.0, 0, []
+    for model, dim, size in workloads:
+        if t_total > budget_s:
+            break
+        cpu_size = min(size, 1024 if dim == 2 else 256)
+        try:
+            dt = oracle.heightmap_cpu_ms(load_tape(model), dim, cpu_size, threads)
+        except Exception as e:          # the stand-in is optional test infrastructure
+            sample.append(f"{model}: unavailable ({e})")
+            continue
+        scale = (size / cpu_size) ** 2              # a heightmap renderer's work follows the visible surface: ~ size^2
+        t_total += dt * scale * 1e-3
+        frames += 1
+        sample.append(f"{model}_{dim}d: {dt:.1f} ms measured at {cpu_size}, x{scale:.0f} -> {dt * scale:.0f} ms at {size}")
+    if frames:
+        out.update({"value": t_total * 1e3 / frames,
+                    "sample": "libfive-algorithm CPU stand-in (not libfive: unbuildable here), one frame of each workload "
+                              "at a bounded size, scaled by (size ratio)^2 (" + "; ".join(sample) + ")"})
+    # (b) the GPU algorithm restated on the CPU (oracle/mpr_oracle.c), full size
+    t_total, frames, sample = 0.0, 0, []
     for model, dim, size in workloads:
         if t_total > budget_s:
             break
@@ -111,8 +147,26 @@ def cpu_baseline(workloads, budget_s: float = 60.0) -> dict:
         t_total += dt
         frames += 1
         sample.append(f"{model}_{dim}d_{size}: {dt * 1e3:.1f} ms")
-    return {"value": t_total * 1e3 / max(frames, 1), "unit": "ms/frame", "cores": threads, "kind": "port",
+    port = {"value": t_total * 1e3 / max(frames, 1), "unit": "ms/frame", "cores": threads,
             "sample": "one frame of each workload, oracle/mpr_oracle.c with OpenMP over tiles (" + "; ".join(sample) + ")"}
+    out["gpu_algorithm_port"] = port
+    if "value" not in out:
+        out.update({"value": port["value"], "sample": port["sample"]})
+    return out
+
+
+def golden_digest(case: str):
+    """sha of the reference build's image / normals for this case (tests/golden/ref, minted from oracle/_ref)."""
+    f = ROOT / "tests" / "golden" / "ref" / f"{case}.json"
+    if not f.exists():
+        return None
+    d = json.loads(f.read_text())
+    return {k: d[k]["sha"] for k in ("image", "normals") if k in d}
+
+
+def digest(a: np.ndarray) -> str:
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:32]
 
 
 # Launch order inside one frame (mpr_b200/csrc/api.cu: render()).
@@ -150,7 +204,11 @@ def run_mine(args, workloads):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("MPRB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL prints its communicator line (rank / nranks) at INFO level; it goes to stderr so that stdout
+        # stays the one JSON line.
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("MPRB_NCCL_DEBUG", "INFO"))
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     class DevArray:   # wraps a raw device pointer for torch.as_tensor
@@ -201,7 +259,9 @@ def run_mine(args, workloads):
 
     def frame_device(job):
         ctx = job["ctx"]
-        (ctx.render2D if job["dim"] == 2 else ctx.render3D)(job["tape"])
+        t0 = time.perf_counter()
+        (ctx.render2D if job["dim"] == 2 else ctx.render3D)(job["tape"])      # returns after the device finished
+        job["wall_ms"] = job.get("wall_ms", 0.0) + (time.perf_counter() - t0) * 1e3
         ms = ctx.stats().gpu_ms
         g = gather(job)
         job["gather_ms"] = job.get("gather_ms", 0.0) + g
@@ -241,7 +301,7 @@ def run_mine(args, workloads):
     for _ in range(args.warmup):
         step(frame_device)
     for j in jobs:                                  # the first exchange includes NCCL's lazy setup
-        j["gather_ms"], j["gather_n"] = 0.0, 0
+        j["gather_ms"], j["gather_n"], j["wall_ms"] = 0.0, 0, 0.0
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -256,6 +316,21 @@ def run_mine(args, workloads):
     e2e = np.array([step(frame_e2e) for _ in range(args.steps)])         # [K, n_jobs] wall ms
     barrier()
     clk = clocks.stop() if rank == 0 else None
+
+    # Every timed frame left its result in place: compare what rank 0 holds (after the exchange when N > 1)
+    # with the reference build's own output for the case (tests/golden/ref/*.json, minted from oracle/_ref).
+    verified, unverified, mismatched = [], [], []
+    if rank == 0:
+        for j in jobs:
+            case = f"{j['model']}_{j['dim']}d_{j['size']}"
+            want = golden_digest(case)
+            if want is None:
+                unverified.append(case)
+                continue
+            got = {"image": digest(j["out_img"].numpy())}
+            if j["dim"] == 3:
+                got["normals"] = digest(j["out_nrm"].numpy().view(np.uint32))
+            (verified if all(got[k] == want[k] for k in got) else mismatched).append(case)
 
     # per-kernel timing + counters on separate frames (events between launches perturb nothing
     # in the timed loops above)
@@ -278,7 +353,9 @@ def run_mine(args, workloads):
         st = ctx.stats()
         stats_one[f"{j['model']}_{j['dim']}d_{j['size']}"] = {
             "n_active": list(st.n_active), "tape_index": st.tape_index, "interval_tiles": list(st.i_tiles),
-            "interval_cells": list(st.i_cells), "float_tiles": st.f_tiles, "float_cells": st.f_cells}
+            "interval_cells": list(st.i_cells), "float_tiles": st.f_tiles, "float_cells": st.f_cells,
+            "float_items": st.f_items, "push_tiles": list(st.p_tiles), "push_cells_logical": list(st.p_kept),
+            "push_cells_written": st.p_written}
 
     # max over ranks, step by step
     if world > 1:
@@ -315,7 +392,9 @@ def run_mine(args, workloads):
                        "parallelism": (f"tile-cyclic 64x64-px screen columns x{world}, 1 NCCL all-gather per frame" if SHARD == "diag"
                                        else f"interleaved 64-px tile rows x{world}, 1 NCCL all-gather per image") if world > 1 else "1 GPU",
                        "num_subtapes": SUBTAPES, "l2": "flushed between steps (256 MiB memset, untimed)",
-                       "timing": "CUDA events on the render stream per frame (+ all-gather events), max over ranks",
+                       "timing": "value: CUDA events on the render stream per frame (+ all-gather events), max over ranks; "
+                                 "wall_ms_per_frame: host clock around the same synchronised call (benchmark/stats.cpp protocol)",
+                       "wall_ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": j["wall_ms"] / args.steps for j in jobs},
                        "ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(dev[:, i].mean()) for i, j in enumerate(jobs)},
                        "e2e_ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(e2e[:, i].mean()) for i, j in enumerate(jobs)},
                        "exchange_ms_per_frame_rank0": {f"{j['model']}_{j['dim']}d_{j['size']}": round(j.get("gather_ms", 0.0) / max(j.get("gather_n", 1), 1), 4) for j in jobs},
@@ -325,6 +404,8 @@ def run_mine(args, workloads):
             "e2e": {"value": float(e2e_step.mean() / n_frames), "unit": "ms/frame", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
+            "frames_verified": (not mismatched) and bool(verified),
+            "frames_verified_detail": {"equal_to_reference_build": verified, "no_fixture": unverified, "MISMATCH": mismatched},
             "kernel_ms_per_step": {k: round(v, 4) for k, v in per_kernel.items()},
             "roofline": roof(dom),
             "roofline_eval_tiles": roof("eval_tiles"),
@@ -334,10 +415,13 @@ def run_mine(args, workloads):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and mismatched:
+        raise SystemExit(f"frames differ from the reference build: {mismatched}")
 
 
 def run_reference(args, workloads):
-    """The unmodified reference CUDA renderer (single GPU, default stream, managed memory)."""
+    """The unmodified reference CUDA renderer (single GPU, default stream, managed memory), timed with the
+    same two clocks and the same host buffers as the other arm."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
@@ -345,49 +429,73 @@ def run_reference(args, workloads):
     if not oracle.ref_available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmpr_ref.so missing (build needs /root/reference)"}))
         return
+    import torch
+    torch.cuda.set_device(0)
     jobs = []
     for model, dim, size in workloads:
         ref = oracle.RefGpu(size)
         cells = load_tape(model)
-        jobs.append(dict(model=model, dim=dim, size=size, ref=ref, cells=cells,
-                         img=np.zeros((size, size), dtype=np.int32),
-                         nrm=np.zeros((size, size), dtype=np.uint32) if dim == 3 else None))
+        out_img = torch.empty((size, size), dtype=torch.int32).pin_memory()
+        out_nrm = torch.empty((size, size), dtype=torch.int32).pin_memory() if dim == 3 else None
+        jobs.append(dict(model=model, dim=dim, size=size, ref=ref, cells=cells, out_img=out_img, out_nrm=out_nrm,
+                         img=out_img.numpy(), nrm=out_nrm.numpy().view(np.uint32) if dim == 3 else None, wall_ms=0.0))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")   # > 126 MB L2, as in the other arm
 
-    def frame(job):     # the reference's own protocol: wall clock around render*, which ends in a device sync
+    def frame(job):
+        # Device time: CUDA events on the legacy default stream, which is where the reference launches
+        # (it has no stream of its own) - the second event lands after its final cudaDeviceSynchronize.
+        # Host wall clock around the same call = the reference's own protocol (benchmark/stats.cpp).
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        (job["ref"].render2D if job["dim"] == 2 else job["ref"].render3D)(job["cells"])
-        return (time.perf_counter() - t0) * 1e3
+        e0.record()
+        (job["ref"].render2D if job["dim"] == 2 else job["ref"].render3D)(job["cells"])     # Tape cached after frame 1
+        e1.record()
+        job["wall_ms"] += (time.perf_counter() - t0) * 1e3
+        e1.synchronize()
+        return e0.elapsed_time(e1)
 
-    def frame_e2e(job):  # + Tape construction from host cells, + download of the result
+    def frame_e2e(job):  # + download of the result into pinned host buffers (the Tape stays cached on the device)
         t0 = time.perf_counter()
-        job["ref"].drop_tapes()
         (job["ref"].render2D if job["dim"] == 2 else job["ref"].render3D)(job["cells"])
         job["ref"].download(job["img"], job["nrm"])
         return (time.perf_counter() - t0) * 1e3
 
+    def step(fn):
+        flush.zero_()
+        torch.cuda.synchronize()
+        return [fn(j) for j in jobs]
+
     for _ in range(args.warmup):
-        [frame(j) for j in jobs]
+        step(frame)
+    for j in jobs:
+        j["wall_ms"] = 0.0
     clocks = ClockSampler(0)
     clocks.start()
-    dev = np.array([[frame(j) for j in jobs] for _ in range(args.steps)])
+    dev = np.array([step(frame) for _ in range(args.steps)])
     for _ in range(min(args.warmup, 3)):
-        [frame_e2e(j) for j in jobs]
-    e2e = np.array([[frame_e2e(j) for j in jobs] for _ in range(args.steps)])
+        step(frame_e2e)
+    e2e = np.array([step(frame_e2e) for _ in range(args.steps)])
     clk = clocks.stop()
     n_frames = len(jobs)
-    h2d = sum(j["cells"].nbytes + (64 if j["dim"] == 3 else 36) for j in jobs)
+    h2d = sum((64 if j["dim"] == 3 else 36) for j in jobs)
     d2h = sum(j["size"] ** 2 * 4 * (2 if j["dim"] == 3 else 1) for j in jobs)
+    name = lambda j: f"{j['model']}_{j['dim']}d_{j['size']}"
     line = {
         "impl": "reference", "metric": METRIC, "value": float(dev.sum(1).mean() / n_frames), "unit": "ms/frame",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(dev.sum(1).mean()),
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "the reference's benchmark models as packed tapes (tests/golden/tapes)",
-        "config": {"workload": "+".join(f"{j['model']}_{j['dim']}d_{j['size']}" for j in jobs), "frames_per_step": n_frames,
+        "config": {"workload": "+".join(name(j) for j in jobs), "frames_per_step": n_frames,
+                   "view": "2D identity, 3D T(3,2)=0.3 (reference table drivers)", "parallelism": "1 GPU",
+                   "num_subtapes": SUBTAPES, "l2": "flushed between steps (256 MiB memset, untimed)",
                    "what": "unmodified reference src/context.cu + context.cpp + gpu_opcode.cu compiled for sm_100a with "
                            "-DBIG_SERVER (oracle/Makefile), driven through oracle/ref_wrap.cu",
-                   "timing": "host wall clock around render2D/render3D incl. its cudaDeviceSynchronize (benchmark/stats.cpp protocol)",
-                   "ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(dev[:, i].mean()) for i, j in enumerate(jobs)},
-                   "e2e_ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(e2e[:, i].mean()) for i, j in enumerate(jobs)}},
+                   "timing": "value: CUDA events on the default stream around render2D/render3D (which ends in "
+                             "cudaDeviceSynchronize); wall_ms_per_frame: host clock around the same call (benchmark/stats.cpp)",
+                   "wall_ms_per_frame": {name(j): j["wall_ms"] / args.steps for j in jobs},
+                   "ms_per_frame": {name(j): float(dev[:, i].mean()) for i, j in enumerate(jobs)},
+                   "e2e_ms_per_frame": {name(j): float(e2e[:, i].mean()) for i, j in enumerate(jobs)},
+                   "e2e_protocol": "Tape resident on the device (built once), result downloaded into pinned host buffers"},
         "clocks": clk,
         "e2e": {"value": float(e2e.sum(1).mean() / n_frames), "unit": "ms/frame", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
@@ -437,7 +545,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="mine", choices=["mine", "reference"])
-    ap.add_argument("--workload", default="prospero_2d_4096,bear_3d_1024")
+    ap.add_argument("--workload", default="prospero_2d_4096,bear_3d_1024",
+                    help="comma list of <model>_<2d|3d>_<size>, or 'sweep' = the reference's table sizes "
+                         "(prospero 2D 256..4096, bear 3D 256..1536)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

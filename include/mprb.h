@@ -71,6 +71,14 @@ typedef struct mprb_ctx_opts {
      * (y + x) % row_mod == row_rem - diagonal stripes of 64x64-px screen columns, the finest
      * independent unit (a 3D column keeps all its z tiles).  0 = whole rows, as above. */
     int32_t col_step;
+    /* One context over n_gpus devices of this process (device, device + 1, ...; peer access to
+     * `device` required): each renders the screen columns (x + y) % n_gpus == its index and writes
+     * its blocks of the final image / normals straight into `device`'s buffers over NVLink, so after a
+     * render call stages[3].filled and normals hold the whole frame there (the other stages describe
+     * device 0's share only).  0 = take the count from the environment variable MPRB_GPUS (default 1),
+     * which is how the reference's unchanged drivers, whose mpr::Context(int) knows nothing of
+     * devices, are put on several GPUs.  Not to be combined with the row_* options. */
+    int32_t n_gpus;
 } mprb_ctx_opts;
 
 /* Per-frame counters, filled by the render calls (device-side; no extra syncs). */
@@ -90,6 +98,9 @@ typedef struct mprb_frame_stats {
     float gpu_ms;             /* device time of the whole frame (CUDA events) */
     float kernel_ms[12];      /* device time per launch (only when timing is enabled) */
     int32_t n_launches;       /* kernels launched for the frame */
+    uint64_t f_items;         /* float-stage work items: runs of up to 2 (4) tiles that share one tape */
+    uint64_t p_written;       /* arena cells actually written by pushes: sibling tiles whose verdicts
+                                 agree share ONE copy of their shortened tape (p_kept counts it per tile) */
 } mprb_frame_stats;
 
 /* ---- context: mpr::Context::Context(int32_t) (src/context.cpp:16-49) ------------ */

@@ -45,6 +45,7 @@ class CtxOpts(C.Structure):
         ("row_mod", C.c_int32),
         ("row_rem", C.c_int32),
         ("col_step", C.c_int32),
+        ("n_gpus", C.c_int32),
     ]
 
 
@@ -65,6 +66,8 @@ class FrameStats(C.Structure):
         ("gpu_ms", C.c_float),
         ("kernel_ms", C.c_float * 12),
         ("n_launches", C.c_int32),
+        ("f_items", C.c_uint64),
+        ("p_written", C.c_uint64),
     ]
 
     def asdict(self):
@@ -256,15 +259,23 @@ class Effects:
         _check(lib().mprb_effects_buffers(self._h, C.byref(img), None))
         return np.ctypeslib.as_array(img, shape=(self._size, self._size))
 
+    def tmp(self):
+        tmp = C.POINTER(C.c_int32)()
+        _check(lib().mprb_effects_buffers(self._h, None, C.byref(tmp)))
+        return np.ctypeslib.as_array(tmp, shape=(self._size, self._size))
+
 
 class Context:
     """Mirror of mpr::Context (reference inc/context.hpp:38-73)."""
 
     def __init__(self, image_size_px: int, device: int = -1, num_subtapes: int = 0,
-                 row_begin: int = 0, row_end: int = 0, row_mod: int = 0, row_rem: int = 0, col_step: int = 0):
+                 row_begin: int = 0, row_end: int = 0, row_mod: int = 0, row_rem: int = 0, col_step: int = 0,
+                 n_gpus: int = 1):
+        """n_gpus > 1: one context over that many devices of this process (see include/mprb.h);
+        n_gpus = 0 takes the count from MPRB_GPUS, like mpr::Context does."""
         self.image_size_px = image_size_px
         self._h = C.c_void_p()
-        opts = CtxOpts(device, num_subtapes, row_begin, row_end, row_mod, row_rem, col_step)
+        opts = CtxOpts(device, num_subtapes, row_begin, row_end, row_mod, row_rem, col_step, n_gpus)
         _check(lib().mprb_ctx_create(image_size_px, C.byref(opts), C.byref(self._h)))
 
     def close(self):

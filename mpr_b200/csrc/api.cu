@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -72,20 +73,31 @@ cudaError_t managed_alloc(T** out, size_t count, int device) {
 
 }  // namespace
 
+// Device-side copies of a tape: made once per device that renders it (a multi-GPU context walks the
+// same Tape on every device; a plain cudaMalloc on "whatever device is current" would leave the others
+// dereferencing memory they cannot reach).
+struct TapeDev {
+    uint64_t* cells = nullptr;       // the contiguous cells (k_eval_root's sweep reads them)
+    uint64_t* chunked = nullptr;     // the same tape in chunk-terminated layout (tape_stream.cuh)
+    RootClause* sched = nullptr;     // clause-parallel plan for the root level (see k_eval_root)
+    int32_t* level_start = nullptr;
+    int32_t group = 0;               // threads per tile; 0 = no plan (serial root walk)
+    int32_t smem_per_tile = 0;
+};
+
 struct mprb_tape {
     uint64_t* cells = nullptr;   // managed; the cells as given (Tape::data)
     int32_t length = 0;
-    uint64_t* chunked = nullptr; // device; the same tape in chunk-terminated layout (tape_stream.cuh)
     int32_t n_chunked = 0;
+    std::vector<uint64_t> host_cells;
     std::vector<uint64_t> host_chunked;
     int32_t n_slots = 0;
-    // Clause-parallel plan for the root level (see k_eval_root)
-    RootClause* sched = nullptr;        // device
-    int32_t* level_start = nullptr;     // device
+    std::vector<RootClause> sched;       // host copy of the root plan
+    std::vector<int32_t> level_start;
     int32_t n_levels = 0;
     int32_t result_v = 0;
-    int32_t group = 0;                  // threads per tile; 0 = no plan (serial root walk)
-    int32_t smem_per_tile = 0;
+    mutable std::mutex mu;
+    mutable std::map<int, TapeDev> dev;  // by CUDA device ordinal
 };
 
 struct mprb_ctx {
@@ -111,6 +123,7 @@ struct mprb_ctx {
 
     // internal
     int32_t* active_list[3] = {};
+    int32_t* float_items = nullptr;  // device: work items of the float pass (runs of tiles sharing a tape)
     FrameCtl* ctl = nullptr;
     FrameCtl* ctl_host = nullptr;    // pinned
     uint64_t* stage_cells = nullptr; // pinned staging for host tapes
@@ -126,6 +139,10 @@ struct mprb_ctx {
 
     mprb_frame_stats stats = {};
     std::map<long long, int> occ_cache;
+
+    // multi-GPU: sub-contexts on the other devices (owned by this, the primary, context)
+    std::vector<mprb_ctx*> peers;
+    cudaEvent_t ev_body = nullptr;   // the frame's kernels are enqueued up to here (no timing)
 };
 
 namespace {
@@ -236,6 +253,48 @@ RootPlan build_root_plan(const uint64_t* cells, int32_t n_cells) {
     return p;
 }
 
+// The device-side copies of `t` on `device` (which must be current); null on a CUDA error.
+const TapeDev* tape_on(const mprb_tape* t, int device) {
+    std::lock_guard<std::mutex> lock(t->mu);
+    auto it = t->dev.find(device);
+    if (it != t->dev.end()) return &it->second;
+    TapeDev d;
+    auto upload = [](auto** dst, const auto& v) {
+        typedef typename std::remove_reference<decltype(v[0])>::type T;
+        cudaError_t e = cudaMalloc(dst, sizeof(T) * std::max<size_t>(v.size(), 1));
+        if (e == cudaSuccess && !v.empty()) e = cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
+        return e;
+    };
+    cudaError_t e = upload(&d.cells, t->host_cells);
+    if (e == cudaSuccess) e = upload(&d.chunked, t->host_chunked);
+    const int n = t->length - 2;
+    if (e == cudaSuccess && !t->sched.empty()) {
+        // Threads per tile ~ clauses per level, so that a level is one pass; bounded by what one
+        // CTA's shared memory holds on THIS device.
+        int group = 32;
+        while (group < kRootThreads && group < n / std::max(t->n_levels, 1)) group *= 2;
+        const int per_tile = ((n + 4) * 10 + 64 + 15) / 16 * 16;
+        int max_smem = 0;
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        while (group < kRootThreads && (kRootThreads / group) * per_tile > max_smem) group *= 2;
+        if (per_tile <= max_smem) {
+            e = upload(&d.sched, t->sched);
+            if (e == cudaSuccess) e = upload(&d.level_start, t->level_start);
+            d.group = group;
+            d.smem_per_tile = per_tile;
+        }
+    }
+    if (e != cudaSuccess) {
+        if (d.cells) cudaFree(d.cells);
+        if (d.chunked) cudaFree(d.chunked);
+        if (d.sched) cudaFree(d.sched);
+        if (d.level_start) cudaFree(d.level_start);
+        fail(MPRB_E_CUDA, "tape upload to device %d: %s", device, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return &(t->dev[device] = d);
+}
+
 int ensure_stage(mprb_ctx* c, int stage, long long cap) {
     if (c->tiles_cap[stage] >= cap) return MPRB_OK;
     if (c->tiles[stage]) cudaFree(c->tiles[stage]);
@@ -246,17 +305,21 @@ int ensure_stage(mprb_ctx* c, int stage, long long cap) {
         if (c->active_list[stage]) cudaFree(c->active_list[stage]);
         c->active_list[stage] = nullptr;
         MPRB_CUDA(cudaMalloc(&c->active_list[stage], sizeof(int32_t) * size_t(cap)));
+    } else {
+        if (c->float_items) cudaFree(c->float_items);
+        c->float_items = nullptr;
+        MPRB_CUDA(cudaMalloc(&c->float_items, sizeof(int32_t) * size_t(cap)));
     }
     return MPRB_OK;
 }
 
-int cached_occupancy(mprb_ctx* c, int kind, int dim, bool root, int n_slots) {
-    const long long key = (long long)kind << 40 | (long long)dim << 32 | (long long)root << 24 | n_slots;
+int cached_occupancy(mprb_ctx* c, int kind, int dim, bool root, int n_slots, int group = 1) {
+    const long long key = (long long)kind << 40 | (long long)dim << 32 | (long long)root << 24 | (long long)group << 16 | n_slots;
     auto itr = c->occ_cache.find(key);
     if (itr != c->occ_cache.end()) return itr->second;
     int n = 0;
     if (kind == 0) n = occupancy_eval_tiles(dim, root, n_slots);
-    else if (kind == 1) n = occupancy_eval_voxels(dim, n_slots);
+    else if (kind == 1) n = occupancy_eval_voxels(dim, n_slots, group);
     else n = occupancy_normals(n_slots);
     n = std::max(n, 1);
     c->occ_cache[key] = n;
@@ -281,6 +344,8 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
     const int S = c->size;
     cudaStream_t s = c->stream;
     MPRB_CUDA(cudaSetDevice(c->device));
+    const TapeDev* td = tape_on(plan, c->device);
+    if (!td) return MPRB_E_CUDA;
     const int32_t n_cells = plan->length;
     const int32_t n_chunked = plan->n_chunked;
     const int n_slots = plan->n_slots;
@@ -328,7 +393,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         MPRB_CUDA(cudaMemcpyAsync(c->arena, c->stage_cells, sizeof(uint64_t) * size_t(n_chunked),
                                   cudaMemcpyHostToDevice, s));
     } else {
-        MPRB_CUDA(cudaMemcpyAsync(c->arena, plan->chunked, sizeof(uint64_t) * size_t(n_chunked),
+        MPRB_CUDA(cudaMemcpyAsync(c->arena, td->chunked, sizeof(uint64_t) * size_t(n_chunked),
                                   cudaMemcpyDeviceToDevice, s));
     }
     MPRB_CUDA(cudaMemsetAsync(c->filled[0], 0, sizeof(int32_t) * size_t(tps0) * tps0, s));
@@ -342,14 +407,15 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
 
     int q = 0;
     const int small_grid = c->sm_count * 4;
+    const int group = float_group(n_slots, heat);      // tiles per work item of the float pass
     if (brute) {
         // Context::render2D_brute (context.cu:1461-1508): no interval levels; every 8x8 tile goes
         // to the float pass with the root tape.
         const long long count = (long long)(S / 8) * (S / 8);
         if (int e = ensure_stage(c, 3, count)) return e;
         MPRB_CUDA(cudaMemsetAsync(c->filled[3], 0, sizeof(int32_t) * size_t(S) * S, s));
-        launch_preload_tiles(c->tiles[3], int32_t(count), &c->ctl->n_active[n_levels - 1],
-                             int(std::min<long long>(small_grid, (count + 255) / 256)), s);
+        launch_preload_tiles(c->tiles[3], c->float_items, int32_t(count), &c->ctl->n_active[n_levels - 1],
+                             &c->ctl->n_active[3], int(std::min<long long>(small_grid, (count + 255) / 256)), s);
         tm.mark();
     }
     for (int l = 0; l < n_levels && !brute; ++l) {
@@ -387,7 +453,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         ea.heat = heat_units;
         ea.heat_px = px_of[l];
         ea.n_root = n_cells - 2;
-        if (root && plan->group > 0 && !c->serial_root && !heat) {
+        if (root && td->group > 0 && !c->serial_root && !heat) {
             EvalRootArgs ra = {};
             ra.arena = c->arena;
             ra.tape_index = &c->ctl->tape_cursor;
@@ -402,14 +468,14 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
             ra.row_rem = c->row_rem;
             ra.col_step = c->col_step;
             ra.ctl = c->ctl;
-            ra.cells = plan->cells;
-            ra.sched = plan->sched;
-            ra.level_start = plan->level_start;
+            ra.cells = td->cells;
+            ra.sched = td->sched;
+            ra.level_start = td->level_start;
             ra.n_levels = plan->n_levels;
             ra.n_clauses = n_cells - 2;
             ra.result_v = plan->result_v;
-            ra.group = plan->group;
-            ra.smem_per_tile = plan->smem_per_tile;
+            ra.group = td->group;
+            ra.smem_per_tile = td->smem_per_tile;
             ra.z = z;
             launch_eval_root(dim, ra, mat, s);
         } else {
@@ -432,6 +498,9 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         ra.n_active = &c->ctl->n_active[l];
         ra.active_list = c->active_list[st];
         ra.out_tiles = c->tiles[3];
+        ra.items = c->float_items;
+        ra.n_items = &c->ctl->n_active[3];
+        ra.gmax = group;
         ra.next_cap = last ? c->tiles_cap[3] : c->tiles_cap[stage_of[l + 1]];
         ra.last_level = last ? 1 : 0;
         ra.level = l;
@@ -455,7 +524,9 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         va.image = c->filled[3];
         va.tiles = c->tiles[3];
         va.tiles_cap = int32_t(std::min<long long>(c->tiles_cap[3], INT32_MAX));
-        va.n_tiles = &c->ctl->n_active[n_levels - 1];
+        va.items = c->float_items;
+        va.n_items = &c->ctl->n_active[3];
+        va.group = brute ? 1 : group;
         va.tps = uint32_t(S / px_of[n_levels - 1]);
         va.ctl = c->ctl;
         va.queue = &c->ctl->queue[q++];
@@ -464,7 +535,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         va.z = z;
         va.heat = heat_units;
         va.n_root = n_cells - 2;
-        const int grid = c->sm_count * cached_occupancy(c, 1, dim, false, n_slots);
+        const int grid = c->sm_count * cached_occupancy(c, 1, dim, false, n_slots, va.group);
         if (dim == 2) launch_eval_pixels(va, m3, grid, s);
         else launch_eval_voxels(va, m4, grid, s);
         tm.mark();
@@ -486,11 +557,52 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         launch_normals(na, m4, c->sm_count * cached_occupancy(c, 2, 3, false, n_slots), s);
         tm.mark();
     }
-    MPRB_CUDA(cudaMemcpyAsync(c->ctl_host, c->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
-    cudaEventRecord(c->ev_end, s);
     c->stats.n_launches = tm.n - 1;
     MPRB_CUDA(cudaGetLastError());
     return MPRB_OK;
+}
+
+// Closes the frame on the context's stream: counters to the host, end-of-frame event.
+int end_frame(mprb_ctx* c) {
+    MPRB_CUDA(cudaSetDevice(c->device));
+    MPRB_CUDA(cudaMemcpyAsync(c->ctl_host, c->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, c->stream));
+    MPRB_CUDA(cudaEventRecord(c->ev_end, c->stream));
+    return MPRB_OK;
+}
+
+// One frame on every device of the context.  A multi-GPU context (mprb_ctx_opts::n_gpus / MPRB_GPUS)
+// is a primary plus one sub-context per further device, each rendering the 64x64-px screen columns
+// (x + y) % N == its index on its own stream, arena and tile lists - nothing is exchanged during the
+// frame.  When a peer is done it writes the depth and normal blocks it owns STRAIGHT INTO the
+// primary's full-size images over NVLink (k_publish: peer-to-peer stores, no staging buffer, no
+// pack / unpack), and the primary's stream waits for those stores; so stages[3].filled and normals
+// hold the whole frame on the primary device, which is all a caller of the reference's surface
+// ever looks at.  The tile lists and per-level images of a multi-GPU context cover the primary's
+// columns only.
+int render_all(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, const float* matrix, float z,
+               bool heat = false, bool brute = false)
+{
+    if (!c || !plan) return fail(MPRB_E_ARG, "null context or tape");
+    if (c->peers.empty()) {
+        if (int e = render(c, dim, plan, cells_on_host, matrix, z, heat, brute)) return e;
+        return end_frame(c);
+    }
+    if (heat || brute) return fail(MPRB_E_ARG, "the analysis variants (brute, heatmap) run on single-GPU contexts only");
+    if (int e = render(c, dim, plan, cells_on_host, matrix, z)) return e;
+    MPRB_CUDA(cudaEventRecord(c->ev_body, c->stream));           // the primary no longer touches its images
+    for (mprb_ctx* p : c->peers) {
+        if (int e = render(p, dim, plan, cells_on_host, matrix, z)) return e;
+        MPRB_CUDA(cudaStreamWaitEvent(p->stream, c->ev_body, 0));
+        launch_publish(p->size, p->row_mod, p->row_rem, dim, p->filled[3], p->normals, c->filled[3], c->normals,
+                       p->stream);
+        MPRB_CUDA(cudaEventRecord(p->ev_body, p->stream));
+        MPRB_CUDA(cudaGetLastError());
+    }
+    MPRB_CUDA(cudaSetDevice(c->device));
+    for (mprb_ctx* p : c->peers) MPRB_CUDA(cudaStreamWaitEvent(c->stream, p->ev_body, 0));
+    for (mprb_ctx* p : c->peers)
+        if (int e = end_frame(p)) return e;
+    return end_frame(c);
 }
 
 const mprb_tape* host_plan_for(mprb_ctx* c, const uint64_t* cells, int32_t n) {
@@ -505,7 +617,37 @@ const mprb_tape* host_plan_for(mprb_ctx* c, const uint64_t* cells, int32_t n) {
 }
 
 // Waits for the frame and publishes the counters.
+int finish_one(mprb_ctx* c, int dim);
 int finish(mprb_ctx* c, int dim) {
+    int rc = finish_one(c, dim);
+    for (mprb_ctx* p : c->peers) {
+        const int e = finish_one(p, dim);
+        if (e && !rc) rc = e;
+        // a multi-GPU frame reports the work of all its devices
+        mprb_frame_stats& a = c->stats;
+        const mprb_frame_stats& b = p->stats;
+        for (int i = 0; i < 3; ++i) {
+            a.n_active[i] += b.n_active[i];
+            a.i_tiles[i] += b.i_tiles[i];
+            a.i_cells[i] += b.i_cells[i];
+            a.p_tiles[i] += b.p_tiles[i];
+            a.p_cells[i] += b.p_cells[i];
+            a.p_kept[i] += b.p_kept[i];
+        }
+        a.f_tiles += b.f_tiles;
+        a.f_cells += b.f_cells;
+        a.f_items += b.f_items;
+        a.p_written += b.p_written;
+        a.n_pixels += b.n_pixels;
+        a.n_cells += b.n_cells;
+        a.overflow |= b.overflow;
+        a.n_launches += b.n_launches + 1;      // + its publish kernel
+    }
+    if (!c->peers.empty()) MPRB_CUDA(cudaSetDevice(c->device));
+    return rc;
+}
+int finish_one(mprb_ctx* c, int dim) {
+    MPRB_CUDA(cudaSetDevice(c->device));
     MPRB_CUDA(cudaStreamSynchronize(c->stream));
     const FrameCtl& f = *c->ctl_host;
     mprb_frame_stats& st = c->stats;
@@ -525,6 +667,8 @@ int finish(mprb_ctx* c, int dim) {
     st.f_cells = f.stats[ST_F_CELLS];
     st.n_pixels = f.stats[ST_N_PIXELS];
     st.n_cells = f.stats[ST_N_CELLS];
+    st.f_items = f.stats[ST_F_ITEMS];
+    st.p_written = f.stats[ST_P_WRITTEN];
     st.overflow = f.overflow;
     cudaEventElapsedTime(&st.gpu_ms, c->ev_begin, c->ev_end);
     if (c->timing) {
@@ -560,8 +704,70 @@ extern "C" {
 const char* mprb_last_error(void) { return g_error.c_str(); }
 const char* mprb_version(void) { return "mprb 0.1 (sm_100a)"; }
 
+static int create_one(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx** out);
+
 int mprb_ctx_create(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx** out) {
     if (!out) return fail(MPRB_E_ARG, "null out pointer");
+    *out = nullptr;
+    int n_gpus = opts ? opts->n_gpus : 0;
+    if (n_gpus <= 0) {                       // callers of the reference's surface (mpr::Context) pass none
+        const char* env = getenv("MPRB_GPUS");
+        n_gpus = env ? atoi(env) : 1;
+    }
+    if (n_gpus <= 1) return create_one(image_size_px, opts, out);
+
+    // ---- one context spanning n_gpus devices of this process ------------------------------------
+    if (opts && (opts->row_mod > 1 || opts->row_begin != 0 || opts->row_end != 0))
+        return fail(MPRB_E_ARG, "n_gpus > 1 shards the frame itself; do not combine it with row_* options");
+    int first = opts ? opts->device : -1, n_dev = 0;
+    if (first < 0) MPRB_CUDA(cudaGetDevice(&first));
+    MPRB_CUDA(cudaGetDeviceCount(&n_dev));
+    if (first + n_gpus > n_dev)
+        return fail(MPRB_E_ARG, "n_gpus = %d from device %d, but only %d devices are visible", n_gpus, first, n_dev);
+    for (int i = 1; i < n_gpus; ++i) {
+        int can = 0;
+        MPRB_CUDA(cudaDeviceCanAccessPeer(&can, first + i, first));
+        if (!can) return fail(MPRB_E_ARG, "device %d cannot write device %d's memory (no peer access)", first + i, first);
+    }
+    mprb_ctx_opts o = {};
+    if (opts) o = *opts;
+    o.n_gpus = 1;
+    o.row_begin = 0;
+    o.row_end = 0;
+    o.row_mod = n_gpus;
+    o.col_step = 1;
+    mprb_ctx* primary = nullptr;
+    for (int i = 0; i < n_gpus; ++i) {
+        o.device = first + i;
+        o.row_rem = i;
+        mprb_ctx* sub = nullptr;
+        if (int e = create_one(image_size_px, &o, &sub)) {
+            if (primary) mprb_ctx_destroy(primary);
+            return e;
+        }
+        if (i == 0) {
+            primary = sub;
+            continue;
+        }
+        primary->peers.push_back(sub);
+        cudaError_t pe = cudaDeviceEnablePeerAccess(first, 0);          // current device = first + i
+        if (pe == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); pe = cudaSuccess; }
+        if (pe != cudaSuccess) {
+            mprb_ctx_destroy(primary);
+            return fail(MPRB_E_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", first + i, first, cudaGetErrorString(pe));
+        }
+        // the peers store into the primary's (managed) frame buffers: map them there, do not migrate
+        const size_t n = size_t(image_size_px) * image_size_px;
+        cudaMemAdvise(primary->filled[3], sizeof(int32_t) * n, cudaMemAdviseSetAccessedBy, first + i);
+        cudaMemAdvise(primary->normals, sizeof(uint32_t) * n, cudaMemAdviseSetAccessedBy, first + i);
+    }
+    cudaGetLastError();
+    MPRB_CUDA(cudaSetDevice(first));
+    *out = primary;
+    return MPRB_OK;
+}
+
+static int create_one(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx** out) {
     *out = nullptr;
     if (image_size_px < 64 || image_size_px % 64 != 0)
         return fail(MPRB_E_ARG, "image_size_px must be a positive multiple of 64 (got %d)", image_size_px);
@@ -603,6 +809,7 @@ int mprb_ctx_create(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx**
         return bail(e, "cudaStreamCreate");
     cudaEventCreate(&c->ev_begin);
     cudaEventCreate(&c->ev_end);
+    cudaEventCreateWithFlags(&c->ev_body, cudaEventDisableTiming);
     for (auto& ev : c->ev_k) cudaEventCreate(&ev);
 
     // Filled images: (S/64)^2, (S/16)^2, (S/4)^2, S^2 (context.cpp:21-26)
@@ -660,6 +867,8 @@ int mprb_ctx_create(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx**
 
 void mprb_ctx_destroy(mprb_ctx* c) {
     if (!c) return;
+    for (mprb_ctx* p : c->peers) mprb_ctx_destroy(p);
+    c->peers.clear();
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 4; ++i) {
@@ -667,6 +876,7 @@ void mprb_ctx_destroy(mprb_ctx* c) {
         if (c->tiles[i]) cudaFree(c->tiles[i]);
     }
     for (int i = 0; i < 3; ++i) if (c->active_list[i]) cudaFree(c->active_list[i]);
+    if (c->float_items) cudaFree(c->float_items);
     if (c->arena) cudaFree(c->arena);
     if (c->tape_index) cudaFree(c->tape_index);
     if (c->num_active_tiles) cudaFree(c->num_active_tiles);
@@ -679,6 +889,7 @@ void mprb_ctx_destroy(mprb_ctx* c) {
     if (c->host_plan) mprb_tape_destroy(c->host_plan);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->ev_body) cudaEventDestroy(c->ev_body);
     for (auto& ev : c->ev_k) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -720,41 +931,25 @@ int mprb_tape_create(const uint64_t* host_cells, int32_t n_cells, mprb_tape** ou
     }
     t->length = n_cells;
     t->n_slots = tape_num_slots(host_cells, n_cells);
+    t->host_cells.assign(host_cells, host_cells + n_cells);
     t->host_chunked = chunk_layout(host_cells, n_cells);
     t->n_chunked = int32_t(t->host_chunked.size());
-    e = cudaMalloc(&t->chunked, sizeof(uint64_t) * t->host_chunked.size());
-    if (e == cudaSuccess)
-        e = cudaMemcpy(t->chunked, t->host_chunked.data(), sizeof(uint64_t) * t->host_chunked.size(),
-                       cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        mprb_tape_destroy(t);
-        return fail(MPRB_E_CUDA, "tape upload: %s", cudaGetErrorString(e));
-    }
     if (n_cells > 2 && n_cells - 2 < (1 << 20)) {
-        const RootPlan plan = build_root_plan(host_cells, n_cells);
-        const int n = n_cells - 2;
-        const int levels = int(plan.level_start.size()) - 1;
-        // Threads per tile ~ clauses per level, so that a level is one pass
-        int group = 32;
-        while (group < kRootThreads && group < n / std::max(levels, 1)) group *= 2;
-        const int per_tile = ((n + 4) * 10 + 64 + 15) / 16 * 16;
-        int max_smem = 0, dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        while (group < kRootThreads && (kRootThreads / group) * per_tile > max_smem) group *= 2;
-        if (per_tile <= max_smem && plan.result_v != 0) {
-            cudaError_t e1 = cudaMalloc(&t->sched, sizeof(RootClause) * plan.sched.size());
-            cudaError_t e2 = cudaMalloc(&t->level_start, sizeof(int32_t) * plan.level_start.size());
-            if (e1 == cudaSuccess && e2 == cudaSuccess) {
-                cudaMemcpy(t->sched, plan.sched.data(), sizeof(RootClause) * plan.sched.size(), cudaMemcpyHostToDevice);
-                cudaMemcpy(t->level_start, plan.level_start.data(), sizeof(int32_t) * plan.level_start.size(),
-                           cudaMemcpyHostToDevice);
-                t->n_levels = levels;
-                t->result_v = plan.result_v;
-                t->group = group;
-                t->smem_per_tile = per_tile;
-            }
+        RootPlan plan = build_root_plan(host_cells, n_cells);
+        if (plan.result_v != 0) {
+            t->n_levels = int(plan.level_start.size()) - 1;
+            t->result_v = plan.result_v;
+            t->sched.swap(plan.sched);
+            t->level_start.swap(plan.level_start);
         }
+    }
+    // Device-side copies are made per device on first use (tape_on); make the current device's now
+    // so that an out-of-memory condition surfaces here.
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!tape_on(t, dev)) {
+        mprb_tape_destroy(t);
+        return MPRB_E_CUDA;
     }
     *out = t;
     return MPRB_OK;
@@ -762,10 +957,18 @@ int mprb_tape_create(const uint64_t* host_cells, int32_t n_cells, mprb_tape** ou
 
 void mprb_tape_destroy(mprb_tape* t) {
     if (!t) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& kv : t->dev) {
+        cudaSetDevice(kv.first);
+        TapeDev& d = kv.second;
+        if (d.cells) cudaFree(d.cells);
+        if (d.chunked) cudaFree(d.chunked);
+        if (d.sched) cudaFree(d.sched);
+        if (d.level_start) cudaFree(d.level_start);
+    }
+    cudaSetDevice(cur);
     if (t->cells) cudaFree(t->cells);
-    if (t->chunked) cudaFree(t->chunked);
-    if (t->sched) cudaFree(t->sched);
-    if (t->level_start) cudaFree(t->level_start);
     delete t;
 }
 
@@ -775,19 +978,19 @@ int32_t mprb_tape_num_slots(const mprb_tape* t) { return t ? t->n_slots : 0; }
 
 int mprb_render2d(mprb_ctx* c, const mprb_tape* t, const float mat3[9], float z) {
     if (!c || !t || !mat3) return fail(MPRB_E_ARG, "null argument");
-    if (int e = render(c, 2, t, false, mat3, z)) return e;
+    if (int e = render_all(c, 2, t, false, mat3, z)) return e;
     return finish(c, 2);
 }
 
 int mprb_render3d(mprb_ctx* c, const mprb_tape* t, const float mat4[16]) {
     if (!c || !t || !mat4) return fail(MPRB_E_ARG, "null argument");
-    if (int e = render(c, 3, t, false, mat4, 0.0f)) return e;
+    if (int e = render_all(c, 3, t, false, mat4, 0.0f)) return e;
     return finish(c, 3);
 }
 
 int mprb_render2d_brute(mprb_ctx* c, const mprb_tape* t, const float mat3[9], float z) {
     if (!c || !t || !mat3) return fail(MPRB_E_ARG, "null argument");
-    if (int e = render(c, 2, t, false, mat3, z, false, true)) return e;
+    if (int e = render_all(c, 2, t, false, mat3, z, false, true)) return e;
     return finish(c, 2);
 }
 
@@ -804,7 +1007,7 @@ static int heatmap_out(mprb_ctx* c, const mprb_tape* t, float** out) {
 
 int mprb_render2d_heatmap(mprb_ctx* c, const mprb_tape* t, const float mat3[9], float z, float** heatmap) {
     if (!c || !t || !mat3 || !heatmap) return fail(MPRB_E_ARG, "null argument");
-    if (int e = render(c, 2, t, false, mat3, z, true)) return e;
+    if (int e = render_all(c, 2, t, false, mat3, z, true)) return e;
     if (int e = heatmap_out(c, t, heatmap)) return e;
     const int e = finish(c, 2);
     if (e) {              // e.g. a tile list overflowed: the caller gets no half-valid buffer to free
@@ -816,7 +1019,7 @@ int mprb_render2d_heatmap(mprb_ctx* c, const mprb_tape* t, const float mat3[9], 
 
 int mprb_render3d_heatmap(mprb_ctx* c, const mprb_tape* t, const float mat4[16], float** heatmap) {
     if (!c || !t || !mat4 || !heatmap) return fail(MPRB_E_ARG, "null argument");
-    if (int e = render(c, 3, t, false, mat4, 0.0f, true)) return e;
+    if (int e = render_all(c, 3, t, false, mat4, 0.0f, true)) return e;
     if (int e = heatmap_out(c, t, heatmap)) return e;
     const int e = finish(c, 3);
     if (e) {              // e.g. a tile list overflowed: the caller gets no half-valid buffer to free
@@ -832,7 +1035,7 @@ int mprb_render2d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
     if (int e = validate_tape(host_cells, n_cells)) return e;
     const mprb_tape* t = host_plan_for(c, host_cells, n_cells);
     if (!t) return MPRB_E_CUDA;
-    if (int e = render(c, 2, t, true, mat3, z)) return e;
+    if (int e = render_all(c, 2, t, true, mat3, z)) return e;
     const size_t n = size_t(c->size) * c->size;
     if (image_out)
         MPRB_CUDA(cudaMemcpyAsync(image_out, c->filled[3], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -845,7 +1048,7 @@ int mprb_render3d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
     if (int e = validate_tape(host_cells, n_cells)) return e;
     const mprb_tape* t = host_plan_for(c, host_cells, n_cells);
     if (!t) return MPRB_E_CUDA;
-    if (int e = render(c, 3, t, true, mat4, 0.0f)) return e;
+    if (int e = render_all(c, 3, t, true, mat4, 0.0f)) return e;
     const size_t n = size_t(c->size) * c->size;
     if (depth_out)
         MPRB_CUDA(cudaMemcpyAsync(depth_out, c->filled[3], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));

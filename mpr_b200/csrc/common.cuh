@@ -46,14 +46,16 @@ enum : int {
     ST_F_CELLS = 16,   // float-stage cells visited, summed over tiles
     ST_N_PIXELS = 17,  // normal-pass pixels evaluated
     ST_N_CELLS = 18,   // normal-pass cells visited, summed over pixels
-    ST_COUNT = 20,
+    ST_F_ITEMS = 19,   // float-stage work items (runs of tiles sharing a tape, walked together)
+    ST_P_WRITTEN = 20, // arena cells actually written by pushes (tiles with equal verdicts share one tape)
+    ST_COUNT = 22,
 };
 
 // Device-resident per-frame control block.  Everything the host would
 // otherwise have to read back between levels lives here, so a frame is one
 // uninterrupted stream of launches.
 struct FrameCtl {
-    int32_t n_active[4];   // [i] = tiles still ambiguous after interval level i
+    int32_t n_active[4];   // [i] = tiles still ambiguous after interval level i; [3] = float-pass work items
     int32_t queue[10];     // work-queue heads, one per persistent launch
     int32_t overflow;      // bit i set: tile array of stage i+1 too small
     int32_t tape_cursor;   // arena allocation cursor in cells (the reference's *tape_index)

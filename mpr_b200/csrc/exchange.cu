@@ -83,7 +83,36 @@ k_exchange(const ExchangeGeom g, int rank, int32_t* __restrict__ depth, uint32_t
     }
 }
 
+// Multi-GPU context inside one process (api.cu: render_all): device `rank` of `world` copies the
+// 64x64-px blocks it owns - tiles with (x + y) % world == rank - from its own frame into the
+// primary device's frame with plain stores through the peer mapping (NVLink): 128-bit rows, one CTA
+// per (tile, plane), no intermediate buffer on either side.
+__global__ void __launch_bounds__(256)
+k_publish(int size, int tiles, int world, int rank, const int32_t* __restrict__ depth, const uint32_t* __restrict__ normals,
+          int32_t* __restrict__ peer_depth, uint32_t* __restrict__ peer_normals)
+{
+    const int per_row = (tiles + world - 1) / world;
+    const int ty = blockIdx.x / per_row;
+    const int tx = (((rank - ty) % world) + world) % world + (blockIdx.x % per_row) * world;
+    if (tx >= tiles) return;
+    const size_t px0 = size_t(ty) * 64 * size + size_t(tx) * 64;
+    const uint4* src = reinterpret_cast<const uint4*>(blockIdx.y == 0 ? reinterpret_cast<const uint32_t*>(depth) : normals);
+    uint4* dst = reinterpret_cast<uint4*>(blockIdx.y == 0 ? reinterpret_cast<uint32_t*>(peer_depth) : peer_normals);
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {          // 64 rows of 16 x 16 bytes
+        const size_t o = (px0 + size_t(i >> 4) * size) / 4 + (i & 15);
+        dst[o] = src[o];
+    }
+}
+
 }  // namespace
+
+void launch_publish(int size, int world, int rank, int dim, const int32_t* depth, const uint32_t* normals,
+                    int32_t* peer_depth, uint32_t* peer_normals, cudaStream_t s) {
+    const int tiles = size / 64;
+    const int per_row = (tiles + world - 1) / world;
+    k_publish<<<dim3(tiles * per_row, dim == 3 ? 2 : 1), 256, 0, s>>>(size, tiles, world, rank, depth, normals, peer_depth,
+                                                                       peer_normals);
+}
 
 size_t exchange_rank_bytes(int size, int world, int dim) {
     const int tiles = size / 64;

@@ -32,6 +32,8 @@
 // scheduled (work units, memory layout, fusion, queues) is specific to this
 // implementation.
 #include <cstdint>
+#include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "deriv.cuh"
@@ -195,11 +197,11 @@ static_assert(kFastOps == (((1u << 30) - 1) & ~((1u << OP_END) | (1u << OP_JUMP)
 // will run it.  A hint only ever relates a cell to its neighbour in memory, and the loop
 // only ever runs a cell right after that neighbour (entries land after an END / JUMP / slow
 // cell, which never forward), so stale cells elsewhere in the chunk do not matter.
-template <uint32_t FAST, uint32_t LHS, uint32_t RHS>
+template <uint32_t FAST, uint32_t LHS, uint32_t RHS, int SHIFT = 0>
 __device__ __forceinline__ void annotate_chunk(uint32_t buf)
 {
     const int lane = threadIdx.x & 31;
-    uint32_t byte0[2];
+    uint32_t word[2];
     #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const int j = lane + 32 * k;
@@ -217,11 +219,19 @@ __device__ __forceinline__ void annotate_chunk(uint32_t buf)
             }
             if (fast(wn) && ((wn >> 8) & 0xff) == ((w >> 8) & 0xff)) flags |= 0x80;
         }
-        byte0[k] = (w & 0xff) | flags;
+        // SHIFT > 0 (float pass, G = 2 or 4 tiles per warp): slot ids become row offsets in units of
+        // 256 bytes - id * G - so that the walkers' `byte * 256` addressing needs no multiply.  Ids
+        // are below 32 here (no renaming), so the bytes cannot run into each other.
+        word[k] = (w & 0xff) | flags | ((w & 0xffffff00u) << SHIFT);
     }
     __syncwarp();
-    sts_u8(buf + lane * 8, byte0[0]);
-    sts_u8(buf + (lane + 32) * 8, byte0[1]);
+    if (SHIFT == 0) {
+        sts_u8(buf + lane * 8, word[0]);
+        sts_u8(buf + (lane + 32) * 8, word[1]);
+    } else {
+        sts_u32(buf + lane * 8, word[0]);
+        sts_u32(buf + (lane + 32) * 8, word[1]);
+    }
     __syncwarp();
 }
 
@@ -265,7 +275,7 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
     uint64_t* const arena = a.arena;
     uint32_t choices[kMaxChoices / 16];   // 2 bits per recorded min/max verdict
     // statistics accumulate per warp and are flushed once (one atomic per counter per warp)
-    unsigned long long st_tiles = 0, st_cells = 0, st_ptiles = 0, st_pcells = 0, st_kept = 0;
+    unsigned long long st_tiles = 0, st_cells = 0, st_ptiles = 0, st_pcells = 0, st_kept = 0, st_written = 0;
 
     const int n_items = ROOT ? (a.count0 + 31) / 32 : 2 * min(*a.n_parents, a.tiles_cap / 64);
     const uint32_t tps = a.tps;
@@ -498,6 +508,20 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
             live.set(i_result);
             int o_idx = 0, o_off = 0;
             unsigned kept = 0;
+            // Tiles of this warp that recorded the same verdicts get the same shortened tape (the
+            // push is a function of the parent tape and the verdicts alone), so only the first lane
+            // of each such class writes it and the others point at its copy: the logical tape of
+            // every tile is what the reference's per-thread push produces (context.cu:323-458), the
+            // arena holds it once, and the float pass can walk it once for several tiles.
+            const bool pushed0 = pushing;
+            int writer = lane;
+            {
+                unsigned cls = __ballot_sync(kFull, pushing);
+                const int n_words = (min(n_choice, uint32_t(kMaxChoices)) + 15) >> 4;
+                for (int i = 0; i < n_words; ++i) cls &= __match_any_sync(kFull, choices[i]);
+                if (pushing) writer = __ffs(cls) - 1;
+                pushing = pushing && writer == lane;
+            }
             if (pushing) {
                 if (*(volatile int32_t*)a.tape_index >= cap) {
                     pushing = false;
@@ -512,7 +536,6 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                     }
                 }
             }
-            const bool pushed0 = pushing;
             unsigned bcells = 0;
             int ci = n_choice;
             int cw_index = -1;
@@ -612,10 +635,17 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                 out_tape = o_idx + o_off;
             }
             {
+                st_written += warp_sum(kept);                              // cells that went to the arena
+                // the other members of each class take their writer's tape (or, if the arena ran
+                // out under it, keep the parent tape like it does)
+                const bool w_ok = __shfl_sync(kFull, pushing, writer);
+                const int w_tape = __shfl_sync(kFull, out_tape, writer);
+                const unsigned w_kept = __shfl_sync(kFull, kept, writer);
+                if (pushed0 && writer != lane && w_ok) { out_tape = w_tape; kept = w_kept; }
                 const unsigned n_push = __popc(__ballot_sync(kFull, pushed0));
                 st_ptiles += n_push;
                 st_pcells += (unsigned long long)n_push * bcells;
-                st_kept += warp_sum(pushed0 ? kept : 0u);
+                st_kept += warp_sum(pushed0 ? kept : 0u);                  // per tile, as the reference writes them
             }
             if (HEAT && pushed0) heat_cells += (tape == 0) ? unsigned(a.n_root) : bcells;   // context.cu:1815-1826
         }
@@ -649,6 +679,7 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
             atomicAdd(&a.ctl->stats[ST_P_TILES + a.level], st_ptiles);
             atomicAdd(&a.ctl->stats[ST_P_CELLS + a.level], st_pcells);
             atomicAdd(&a.ctl->stats[ST_P_KEPT + a.level], st_kept);
+            atomicAdd(&a.ctl->stats[ST_P_WRITTEN], st_written);
         }
     }
 }
@@ -924,10 +955,12 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
             }
             out_tape = base;
         }
-        if (t == 0) {
+        if (t == 0 && base >= 0) {                                       // a push that found no room is no push
+            const unsigned long long written = (unsigned long long)(total + 2 + 2 * (n_chunks - 1));
             atomicAdd(&a.ctl->stats[ST_P_TILES], 1ull);
             atomicAdd(&a.ctl->stats[ST_P_CELLS], (unsigned long long)n);
-            atomicAdd(&a.ctl->stats[ST_P_KEPT], (unsigned long long)(base >= 0 ? total + 2 + 2 * (n_chunks - 1) : 0));
+            atomicAdd(&a.ctl->stats[ST_P_KEPT], written);
+            atomicAdd(&a.ctl->stats[ST_P_WRITTEN], written);
         }
     }
     if (t == 0) {
@@ -976,28 +1009,55 @@ k_rank_tiles(const RankArgs a)
         int rank_base = 0;
         if (lane == 0 && m) rank_base = atomicAdd(a.n_active, __popc(m));
         rank_base = __shfl_sync(kFull, rank_base, 0);
-        if (t < n_tiles) {
-            int next = -1;
+        int next = -1;
+        if (!a.last_level) {
             if (active) {
                 const int rank = rank_base + __popc(m & ((1u << lane) - 1));
-                const long long need = a.last_level ? (long long)rank + 1 : ((long long)rank + 1) * 64;
-                if (need > a.next_cap) {
-                    // Next stage's tile array is too small: flag it; the host
-                    // grows the array and renders the frame again.
+                if (((long long)rank + 1) * 64 > a.next_cap) {
+                    // Next stage's tile array is too small: the frame reports MPRB_E_OVERFLOW
                     atomicOr(&a.ctl->overflow, 1 << a.level);
-                } else if (a.last_level) {
-                    // Compact list for the float pass; `next` stays -1 (copy_active_tiles)
-                    a.out_tiles[rank].position = node.position;
-                    a.out_tiles[rank].tape = node.tape;
-                    a.out_tiles[rank].next = -1;
-                }
-                if (!a.last_level) {
+                } else {
                     a.active_list[rank] = t;
                     next = rank;
                 }
             }
-            a.tiles[t].next = next;
+        } else if (m) {
+            // Last level: the compact survivor list for the float pass (copy_active_tiles; `next`
+            // stays -1), ordered so that tiles sharing a tape sit next to each other - these 32 tiles
+            // are siblings, and k_eval_tiles gives siblings with the same verdicts the same tape -
+            // plus one work item per run of up to gmax such tiles.
+            const unsigned cls = active ? __match_any_sync(m, node.tape) : 0u;
+            const int leader = __ffs(cls) - 1;
+            const int within = __popc(cls & ((1u << lane) - 1));
+            const int csize = __popc(cls);
+            const int gmax = a.gmax;
+            int tile_off = 0, item_off = 0, n_items = 0;
+            unsigned leaders = __ballot_sync(kFull, active && lane == leader);
+            while (leaders) {                                  // classes in order of their first lane
+                const int l = __ffs(leaders) - 1;
+                leaders &= leaders - 1;
+                const int sz = __shfl_sync(kFull, csize, l);
+                const int it = (sz + gmax - 1) / gmax;
+                if (l < leader) { tile_off += sz; item_off += it; }
+                n_items += it;
+            }
+            int item_base = 0;
+            if (lane == 0) item_base = atomicAdd(a.n_items, n_items);
+            item_base = __shfl_sync(kFull, item_base, 0);
+            if (active) {
+                const int rank = rank_base + tile_off + within;
+                if ((long long)rank + 1 > a.next_cap) {
+                    atomicOr(&a.ctl->overflow, 1 << a.level);
+                } else {
+                    a.out_tiles[rank].position = node.position;
+                    a.out_tiles[rank].tape = node.tape;
+                    a.out_tiles[rank].next = -1;
+                    if (within % gmax == 0)
+                        a.items[item_base + item_off + within / gmax] = rank * 8 + min(gmax, csize - within);
+                }
+            }
         }
+        if (t < n_tiles) a.tiles[t].next = next;
     }
 }
 
@@ -1044,10 +1104,60 @@ k_upsample_filled(const int32_t* __restrict__ prev, int32_t* __restrict__ image,
 // Runs clauses starting at the cell AFTER `cp` until it meets one it does not handle - END, JUMP,
 // or a trigonometric libdevice function (EXP and LOG are handlers: libdevice's own PTX) - and returns with cp on that cell and its two words
 // in w / imm.  `sb` is this lane's slot base in shared space (slot s at sb + 256 s).
-__device__ __forceinline__ void run_float_clauses(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
+// G = tiles per warp (1, 2 or 4): the same loop over G f32 pairs per slot and lane.
+// U = clauses per trip (1 or 2): see tools/gen_float_loop.py.
+template <int G, int U>
+__device__ __forceinline__ void run_float_clauses(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb);
+template <>
+__device__ __forceinline__ void run_float_clauses<1, 1>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
 {
     asm volatile(
 #include "float_loop_ptx.inc"
+        : "+r"(cp), "=&r"(w), "=&r"(imm)
+        : "r"(sb)
+        : "memory");
+}
+template <>
+__device__ __forceinline__ void run_float_clauses<2, 1>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
+{
+    asm volatile(
+#include "float_loop_ptx_g2.inc"
+        : "+r"(cp), "=&r"(w), "=&r"(imm)
+        : "r"(sb)
+        : "memory");
+}
+template <>
+__device__ __forceinline__ void run_float_clauses<4, 1>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
+{
+    asm volatile(
+#include "float_loop_ptx_g4.inc"
+        : "+r"(cp), "=&r"(w), "=&r"(imm)
+        : "r"(sb)
+        : "memory");
+}
+template <>
+__device__ __forceinline__ void run_float_clauses<1, 2>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
+{
+    asm volatile(
+#include "float_loop_ptx_u2.inc"
+        : "+r"(cp), "=&r"(w), "=&r"(imm)
+        : "r"(sb)
+        : "memory");
+}
+template <>
+__device__ __forceinline__ void run_float_clauses<2, 2>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
+{
+    asm volatile(
+#include "float_loop_ptx_g2u2.inc"
+        : "+r"(cp), "=&r"(w), "=&r"(imm)
+        : "r"(sb)
+        : "memory");
+}
+template <>
+__device__ __forceinline__ void run_float_clauses<4, 2>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
+{
+    asm volatile(
+#include "float_loop_ptx_g4u2.inc"
         : "+r"(cp), "=&r"(w), "=&r"(imm)
         : "r"(sb)
         : "memory");
@@ -1102,10 +1212,16 @@ __device__ __forceinline__ float2 float_clause_libdevice(uint32_t op, float2 L)
     }
 }
 
-template <bool REMAP>
-__device__ __forceinline__ float2 walk_float(TapeStream<REMAP>& ts, int tape, Slots2<REMAP>& slots, unsigned& cells)
+// Walks one tape for the G tiles of a work item (two samples per tile and lane); r[g] receives
+// tile g's result pair.  Slot rows are 32 lanes x 8 G bytes: `sb` is this lane's address in row 0
+// and tile g sits 8 g bytes further.
+template <bool REMAP, int G, int U>
+__device__ __forceinline__ void walk_float(TapeStream<REMAP>& ts, int tape, Slots2<REMAP>& slots, unsigned& cells,
+                                           float2 (&r)[G])
 {
-    if (ts.fetch(tape) && !REMAP) annotate_chunk<kFastOps, kUsesLhs, kUsesRhs>(ts.buf);
+    constexpr int SHIFT = G == 4 ? 2 : (G == 2 ? 1 : 0);
+    static_assert(!REMAP || G == 1, "renamed slots: one tile per warp");
+    if (ts.fetch(tape) && !REMAP) annotate_chunk<kFastOps, kUsesLhs, kUsesRhs, SHIFT>(ts.buf);
     uint32_t cp = ts.rd + ((tape & (kChunk - 1)) << 3);
     uint32_t seg = cp;
     uint32_t w, immb;
@@ -1116,29 +1232,47 @@ __device__ __forceinline__ float2 walk_float(TapeStream<REMAP>& ts, int tape, Sl
             w = d.x;
             immb = d.y;
         } else {
-            run_float_clauses(cp, w, immb, slots.base);
+            run_float_clauses<G, U>(cp, w, immb, slots.base);
         }
         const uint32_t op = w & 0xff;
         if (op <= OP_JUMP) {
             cells += (cp - seg) >> 3;
             if (op == OP_END) { --cells; break; }
             const int t = ts.base + int((cp - ts.rd) >> 3) + int32_t(immb);
-            if (ts.fetch(t) && !REMAP) annotate_chunk<kFastOps, kUsesLhs, kUsesRhs>(ts.buf);
+            if (ts.fetch(t) && !REMAP) annotate_chunk<kFastOps, kUsesLhs, kUsesRhs, SHIFT>(ts.buf);
             cp = ts.rd + ((t & (kChunk - 1)) << 3);
             seg = cp;
             continue;
         }
-        const float2 L = slots.ld(off_lhs2(w));
-        float2 o;
-        if (REMAP) o = float_clause(op, L, slots.ld(off_rhs2(w)), __uint_as_float(immb));
-        else o = float_clause_libdevice(op, L);
-        slots.st(off_out2(w), o);
+        if (REMAP) {
+            const float2 L = slots.ld(off_lhs2(w));
+            slots.st(off_out2(w), float_clause(op, L, slots.ld(off_rhs2(w)), __uint_as_float(immb)));
+        } else {
+            #pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float2 L = lds_f2(slots.base + off_lhs2(w) + 8 * g);
+                sts_f2(slots.base + off_out2(w) + 8 * g, float_clause_libdevice(op, L));
+            }
+        }
     }
-    return slots.ld(off_out2(w));
+    if (REMAP) {
+        r[0] = slots.ld(off_out2(w));
+    } else {
+        #pragma unroll
+        for (int g = 0; g < G; ++g) r[g] = lds_f2(slots.base + off_out2(w) + 8 * g);
+    }
 }
 
-// 2D: one warp per surviving 8x8 tile, two pixels per lane (y and y + 4).
-template <bool REMAP, bool HEAT = false>
+// A work item of the float pass: `count` (1 .. G) tiles of the compact survivor list that share one
+// tape, packed as start * 8 + count (k_rank_tiles writes them).
+__device__ __forceinline__ void unpack_item(int32_t code, int& start, int& count) {
+    code = __shfl_sync(kFull, code, 0);      // every lane loaded the same word; the shuffle tells ptxas so
+    start = code >> 3;
+    count = code & 7;
+}
+
+// 2D: one warp per work item of up to G surviving 8x8 tiles, two pixels per tile and lane (y and y + 4).
+template <bool REMAP, bool HEAT = false, int G = 1, int U = 1>
 __global__ void __launch_bounds__(kFloatMaxThreads)
 k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 {
@@ -1150,57 +1284,79 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
     ts.init(s_dyn + warp * Stream::stride(), a.arena);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
     Slots2<REMAP> slots;
-    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
+    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * G) * 8;
     slots.limit = uint32_t(n_rows) * 256u;
     const uint64_t* const arena = a.arena;
-    unsigned long long st_tiles = 0, st_cells = 0;
+    unsigned long long st_tiles = 0, st_cells = 0, st_items = 0;
     const uint32_t root_hdr = uint32_t(arena[0]);
-    const int n_items = min(*a.n_tiles, a.tiles_cap);
+    const int n_items = min(*a.n_items, a.tiles_cap);
     const uint32_t tps = a.tps;
     const int size = tps * 8;
     const float recip = 1.0f / float(tps * 8u);
     const float* m = mat.d;
+    constexpr int SHIFT = G == 4 ? 2 : (G == 2 ? 1 : 0);
 
     for (;;) {
         const int item = warp_next(a.queue);
         if (item >= n_items) break;
-        const TileNode tile = a.tiles[item];
-        const int tx = tile.position % tps, ty = (tile.position / tps) % tps;
-        const int px = tx * 8 + (lane & 7);
-        const int py = ty * 8 + (lane >> 3);
-        const float fx = sample_coord(px, recip);
-        const float fya = sample_coord(py, recip), fyb = sample_coord(py + 4, recip);
-        const float wa = dot2(m[2], fx, m[5], fya, m[8]);
-        const float wb = dot2(m[2], fx, m[5], fyb, m[8]);
-        const uint32_t h = ts.begin_tape(root_hdr);
-        slots.st(off_out2(h),
-                 make_float2(dot2(m[0], fx, m[3], fya, m[6]) / wa, dot2(m[0], fx, m[3], fyb, m[6]) / wb));
-        slots.st(off_lhs2(h),
-                 make_float2(dot2(m[1], fx, m[4], fya, m[7]) / wa, dot2(m[1], fx, m[4], fyb, m[7]) / wb));
-        slots.st(off_rhs2(h), make_float2(a.z, a.z));
-        unsigned cells = 0;
-        const float2 r = walk_float(ts, tile.tape, slots, cells);
-        if (r.y < 0.0f) a.image[px + (py + 4) * size] = 1;      // context.cu:951-962
-        if (r.x < 0.0f) a.image[px + py * size] = 1;
-        if (HEAT) {                                             // work / 2 on each sample (context.cu:1979-1980)
-            const unsigned long long u = (unsigned long long)(tile.tape == 0 ? unsigned(a.n_root) : cells) * 2048u;
-            atomicAdd(&a.heat[px + size_t(py) * size], u);
-            atomicAdd(&a.heat[px + size_t(py + 4) * size], u);
+        int start, count;
+        unpack_item(__ldg(&a.items[item]), start, count);
+        const int tape = __shfl_sync(kFull, a.tiles[start].tape, 0);   // warp-uniform, and provably so
+        uint32_t h = ts.begin_tape(root_hdr);
+        if (!REMAP) h = (h & 0xff) | ((h & 0xffffff00u) << SHIFT);
+        int px[G], py[G];
+        #pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int position = a.tiles[start + min(g, count - 1)].position;   // short items repeat their last tile
+            const int tx = position % tps, ty = (position / tps) % tps;
+            px[g] = tx * 8 + (lane & 7);
+            py[g] = ty * 8 + (lane >> 3);
+            const float fx = sample_coord(px[g], recip);
+            const float fya = sample_coord(py[g], recip), fyb = sample_coord(py[g] + 4, recip);
+            const float wa = dot2(m[2], fx, m[5], fya, m[8]);
+            const float wb = dot2(m[2], fx, m[5], fyb, m[8]);
+            const float2 X = make_float2(dot2(m[0], fx, m[3], fya, m[6]) / wa, dot2(m[0], fx, m[3], fyb, m[6]) / wb);
+            const float2 Y = make_float2(dot2(m[1], fx, m[4], fya, m[7]) / wa, dot2(m[1], fx, m[4], fyb, m[7]) / wb);
+            if (REMAP) {
+                slots.st(off_out2(h), X);
+                slots.st(off_lhs2(h), Y);
+                slots.st(off_rhs2(h), make_float2(a.z, a.z));
+            } else {
+                sts_f2(slots.base + off_out2(h) + 8 * g, X);
+                sts_f2(slots.base + off_lhs2(h) + 8 * g, Y);
+                sts_f2(slots.base + off_rhs2(h) + 8 * g, make_float2(a.z, a.z));
+            }
         }
-        st_tiles += 1;
-        st_cells += cells;
+        unsigned cells = 0;
+        float2 r[G];
+        walk_float<REMAP, G, U>(ts, tape, slots, cells, r);
+        #pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (g >= count) break;
+            if (r[g].y < 0.0f) a.image[px[g] + (py[g] + 4) * size] = 1;      // context.cu:951-962
+            if (r[g].x < 0.0f) a.image[px[g] + py[g] * size] = 1;
+            if (HEAT) {                                             // work / 2 on each sample (context.cu:1979-1980)
+                const unsigned long long u = (unsigned long long)(tape == 0 ? unsigned(a.n_root) : cells) * 2048u;
+                atomicAdd(&a.heat[px[g] + size_t(py[g]) * size], u);
+                atomicAdd(&a.heat[px[g] + size_t(py[g] + 4) * size], u);
+            }
+        }
+        st_items += 1;
+        st_tiles += count;
+        st_cells += (unsigned long long)cells * count;
     }
     if (lane == 0 && st_tiles) {
         atomicAdd(&a.ctl->stats[ST_F_TILES], st_tiles);
         atomicAdd(&a.ctl->stats[ST_F_CELLS], st_cells);
+        atomicAdd(&a.ctl->stats[ST_F_ITEMS], st_items);
     }
 }
 
-// 3D: one warp per surviving 4x4x4 tile, two voxels per lane (z and z + 2).
+// 3D: one warp per work item of up to G surviving 4x4x4 tiles, two voxels per tile and lane (z and z + 2).
 // Root tiles are issued highest-z first and children inherit that order, so the
 // list is roughly front-to-back and the per-lane early-out below (the
 // reference's, context.cu:852-864) culls most of what lies behind the surface.
-template <bool REMAP, bool HEAT = false>
+template <bool REMAP, bool HEAT = false, int G = 1, int U = 1>
 __global__ void __launch_bounds__(kFloatMaxThreads)
 k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
 {
@@ -1212,57 +1368,87 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
     ts.init(s_dyn + warp * Stream::stride(), a.arena);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
     Slots2<REMAP> slots;
-    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
+    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * G) * 8;
     slots.limit = uint32_t(n_rows) * 256u;
     const uint64_t* const arena = a.arena;
-    unsigned long long st_tiles = 0, st_cells = 0;
+    unsigned long long st_tiles = 0, st_cells = 0, st_items = 0;
     const uint32_t root_hdr = uint32_t(arena[0]);
-    const int n_items = min(*a.n_tiles, a.tiles_cap);
+    const int n_items = min(*a.n_items, a.tiles_cap);
     const uint32_t tps = a.tps;
     const int size = tps * 4;
     const float recip = 1.0f / float(tps * 4u);
     const float* m = mat.d;
+    constexpr int SHIFT = G == 4 ? 2 : (G == 2 ? 1 : 0);
 
     for (;;) {
         const int item = warp_next(a.queue);
         if (item >= n_items) break;
-        const TileNode tile = a.tiles[item];
-        const int tx = tile.position % tps, ty = (tile.position / tps) % tps, tz = (tile.position / tps) / tps;
-        const int px = tx * 4 + (lane & 3);
-        const int py = ty * 4 + ((lane >> 2) & 3);
-        const int pz = tz * 4 + (lane >> 4);            // second sample sits at pz + 2
-        int* const pix = &a.image[px + py * size];
-        // This column already shows something at least as high (context.cu:852-864)
-        const bool alive = __ldcg(pix) < pz + 2;
-        if (!__any_sync(kFull, alive)) continue;
-
-        const float fx = sample_coord(px, recip), fy = sample_coord(py, recip);
-        const float fza = sample_coord(pz, recip), fzb = sample_coord(pz + 2, recip);
-        const float wa = dot3(m[3], fx, m[7], fy, m[11], fza, m[15]);
-        const float wb = dot3(m[3], fx, m[7], fy, m[11], fzb, m[15]);
-        const uint32_t hdr = ts.begin_tape(root_hdr);
-        slots.st(off_out2(hdr), make_float2(dot3(m[0], fx, m[4], fy, m[8], fza, m[12]) / wa,
-                                            dot3(m[0], fx, m[4], fy, m[8], fzb, m[12]) / wb));
-        slots.st(off_lhs2(hdr), make_float2(dot3(m[1], fx, m[5], fy, m[9], fza, m[13]) / wa,
-                                            dot3(m[1], fx, m[5], fy, m[9], fzb, m[13]) / wb));
-        slots.st(off_rhs2(hdr), make_float2(dot3(m[2], fx, m[6], fy, m[10], fza, m[14]) / wa,
-                                            dot3(m[2], fx, m[6], fy, m[10], fzb, m[14]) / wb));
-        unsigned cells = 0;
-        const float2 r = walk_float(ts, tile.tape, slots, cells);
-        if (alive) {
-            // The higher sample wins when both are inside (context.cu:936-948)
-            if (r.y < 0.0f) atomicMax(pix, pz + 2);
-            else if (r.x < 0.0f) atomicMax(pix, pz);
-            if (HEAT)                                           // context.cu:1962
-                atomicAdd(&a.heat[px + size_t(py) * size],
-                          (unsigned long long)(tile.tape == 0 ? unsigned(a.n_root) : cells) * 4096u);
+        int start, count;
+        unpack_item(__ldg(&a.items[item]), start, count);
+        const int tape = __shfl_sync(kFull, a.tiles[start].tape, 0);   // warp-uniform, and provably so
+        int px[G], py[G], pz[G];
+        bool alive[G];
+        bool any = false;
+        #pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int position = a.tiles[start + min(g, count - 1)].position;   // short items repeat their last tile
+            const int tx = position % tps, ty = (position / tps) % tps, tz = (position / tps) / tps;
+            px[g] = tx * 4 + (lane & 3);
+            py[g] = ty * 4 + ((lane >> 2) & 3);
+            pz[g] = tz * 4 + (lane >> 4);            // second sample sits at pz + 2
+            // This column already shows something at least as high (context.cu:852-864)
+            alive[g] = g < count && __ldcg(&a.image[px[g] + py[g] * size]) < pz[g] + 2;
+            any |= alive[g];
         }
-        st_tiles += 1;
-        st_cells += cells;
+        if (!__any_sync(kFull, any)) continue;
+
+        uint32_t hdr = ts.begin_tape(root_hdr);
+        if (!REMAP) hdr = (hdr & 0xff) | ((hdr & 0xffffff00u) << SHIFT);
+        #pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float fx = sample_coord(px[g], recip), fy = sample_coord(py[g], recip);
+            const float fza = sample_coord(pz[g], recip), fzb = sample_coord(pz[g] + 2, recip);
+            const float wa = dot3(m[3], fx, m[7], fy, m[11], fza, m[15]);
+            const float wb = dot3(m[3], fx, m[7], fy, m[11], fzb, m[15]);
+            const float2 X = make_float2(dot3(m[0], fx, m[4], fy, m[8], fza, m[12]) / wa,
+                                         dot3(m[0], fx, m[4], fy, m[8], fzb, m[12]) / wb);
+            const float2 Y = make_float2(dot3(m[1], fx, m[5], fy, m[9], fza, m[13]) / wa,
+                                         dot3(m[1], fx, m[5], fy, m[9], fzb, m[13]) / wb);
+            const float2 Z = make_float2(dot3(m[2], fx, m[6], fy, m[10], fza, m[14]) / wa,
+                                         dot3(m[2], fx, m[6], fy, m[10], fzb, m[14]) / wb);
+            if (REMAP) {
+                slots.st(off_out2(hdr), X);
+                slots.st(off_lhs2(hdr), Y);
+                slots.st(off_rhs2(hdr), Z);
+            } else {
+                sts_f2(slots.base + off_out2(hdr) + 8 * g, X);
+                sts_f2(slots.base + off_lhs2(hdr) + 8 * g, Y);
+                sts_f2(slots.base + off_rhs2(hdr) + 8 * g, Z);
+            }
+        }
+        unsigned cells = 0;
+        float2 r[G];
+        walk_float<REMAP, G, U>(ts, tape, slots, cells, r);
+        #pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (alive[g]) {
+                int* const pix = &a.image[px[g] + py[g] * size];
+                // The higher sample wins when both are inside (context.cu:936-948)
+                if (r[g].y < 0.0f) atomicMax(pix, pz[g] + 2);
+                else if (r[g].x < 0.0f) atomicMax(pix, pz[g]);
+                if (HEAT)                                           // context.cu:1962
+                    atomicAdd(&a.heat[px[g] + size_t(py[g]) * size],
+                              (unsigned long long)(tape == 0 ? unsigned(a.n_root) : cells) * 4096u);
+            }
+        }
+        st_items += 1;
+        st_tiles += count;
+        st_cells += (unsigned long long)cells * count;
     }
     if (lane == 0 && st_tiles) {
         atomicAdd(&a.ctl->stats[ST_F_TILES], st_tiles);
         atomicAdd(&a.ctl->stats[ST_F_CELLS], st_cells);
+        atomicAdd(&a.ctl->stats[ST_F_ITEMS], st_items);
     }
 }
 
@@ -1439,14 +1625,16 @@ __global__ void k_begin_frame(FrameCtl* ctl, int32_t first_free)
 
 // Brute-force frames (reference preload_tiles, context.cu:45-57): every 8x8 tile goes straight
 // to the float pass with the root tape.
-__global__ void k_preload_tiles(TileNode* __restrict__ tiles, int32_t count, int32_t* __restrict__ n_tiles)
+__global__ void k_preload_tiles(TileNode* __restrict__ tiles, int32_t* __restrict__ items, int32_t count,
+                                int32_t* __restrict__ n_tiles, int32_t* __restrict__ n_items)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         tiles[i].position = i;
         tiles[i].tape = 0;
         tiles[i].next = -1;
+        items[i] = i * 8 + 1;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *n_tiles = count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *n_tiles = count; *n_items = count; }
 }
 
 // Work units -> the reference's heatmap value: cells per pixel over the clause count
@@ -1465,8 +1653,8 @@ __global__ void k_heat_finish(const unsigned long long* __restrict__ units, floa
 // Dynamic shared memory of an interval / float tape-walking CTA: per warp one chunk stream plus
 // 256-byte value rows - one per slot id, or kRemapRows when the stream renames slots.
 bool use_remap(int n_slots);
-static size_t walk_smem(int n_rows, bool remap, int warps = kEvalWarps) {
-    return size_t(warps) * (size_t(n_rows) * 256 + (remap ? kStreamStrideRemap : kStreamStridePlain));
+static size_t walk_smem(int n_rows, bool remap, int warps = kEvalWarps, int group = 1) {
+    return size_t(warps) * (size_t(n_rows) * 256 * group + (remap ? kStreamStrideRemap : kStreamStridePlain));
 }
 // Shared-memory value rows per warp: one per slot id, or a fixed budget when slots are renamed.
 int walk_rows(int n_slots) {
@@ -1475,10 +1663,19 @@ int walk_rows(int n_slots) {
     const int rows = env ? atoi(env) : kRemapRowsDefault;
     return rows < kRemapRowsMin ? kRemapRowsMin : (rows > 128 ? 128 : rows);
 }
+// Tiles per work item of the float pass (1, 2 or 4).  Tiles of an item share their tape, and the
+// clause loop is bound by fetch + dispatch, so G tiles cost little more than one - but slot rows
+// grow G-fold and with them the shared memory per warp.  MPRB_FLOAT_GROUP overrides.
+int float_group(int n_slots, bool heat) {
+    if (use_remap(n_slots) || heat) return 1;
+    static const char* env = getenv("MPRB_FLOAT_GROUP");
+    if (env) { const int v = atoi(env); return v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
+    return 1;
+}
 // Warps per CTA of the float pass: the shape that keeps the most warps resident per SM given the
 // per-warp shared memory (value rows + chunk stream), 1 KB the driver reserves per CTA, and the
 // limits of 32 CTAs / 64 warps per SM.  MPRB_FLOAT_WARPS overrides.
-int float_warps(int n_slots) {
+int float_warps(int n_slots, int group) {
     static const char* env = getenv("MPRB_FLOAT_WARPS");
     if (env) { const int v = atoi(env); return v < 1 ? 1 : (v > 32 ? 32 : v); }
     static int smem_per_sm = 0;
@@ -1487,7 +1684,7 @@ int float_warps(int n_slots) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     }
-    const size_t per_warp = walk_smem(walk_rows(n_slots), use_remap(n_slots), 1);
+    const size_t per_warp = walk_smem(walk_rows(n_slots), use_remap(n_slots), 1, group);
     int best = 1, best_resident = 0;
     for (int w = 1; w <= kFloatMaxThreads / 32; ++w) {
         int ctas = int(size_t(smem_per_sm) / (w * per_warp + 1024));
@@ -1514,6 +1711,20 @@ bool use_local_normals(int n_slots) {
     static const char* force = getenv("MPRB_LOCAL_SLOTS");
     if (force) return force[0] == '1';
     return n_slots > 18;
+}
+
+// Float-pass variants without renaming: G tiles per work item x U clauses per loop trip.
+int float_unroll() {
+    static const char* env = getenv("MPRB_FLOAT_UNROLL");
+    return env ? (atoi(env) >= 2 ? 2 : 1) : 1;
+}
+template <typename F> static auto pick_float(int G, int U, F f) {
+    if (G == 4) return U == 2 ? f(std::integral_constant<int, 4>(), std::integral_constant<int, 2>())
+                              : f(std::integral_constant<int, 4>(), std::integral_constant<int, 1>());
+    if (G == 2) return U == 2 ? f(std::integral_constant<int, 2>(), std::integral_constant<int, 2>())
+                              : f(std::integral_constant<int, 2>(), std::integral_constant<int, 1>());
+    return U == 2 ? f(std::integral_constant<int, 1>(), std::integral_constant<int, 2>())
+                  : f(std::integral_constant<int, 1>(), std::integral_constant<int, 1>());
 }
 
 // Also pin the L1/shared split to "all shared" for the shared-memory variants: occupancy there
@@ -1549,8 +1760,13 @@ void init_kernels(int max_smem_optin) {
     opt_in(k_eval_voxels<false, true>, max_smem_optin);
     opt_in(k_eval_pixels<true, true>, max_smem_optin);
     opt_in(k_eval_voxels<true, true>, max_smem_optin);
-    opt_in(k_eval_pixels<false>, max_smem_optin);
-    opt_in(k_eval_voxels<false>, max_smem_optin);
+    for (int G = 1; G <= 4; G *= 2)
+        for (int U = 1; U <= 2; ++U)
+            pick_float(G, U, [&](auto g, auto u) {
+                opt_in(k_eval_pixels<false, false, decltype(g)::value, decltype(u)::value>, max_smem_optin);
+                opt_in(k_eval_voxels<false, false, decltype(g)::value, decltype(u)::value>, max_smem_optin);
+                return 0;
+            });
     opt_in(k_normals<false>, max_smem_optin);
     opt_in(k_eval_pixels<true>, max_smem_optin);
     opt_in(k_eval_voxels<true>, max_smem_optin);
@@ -1599,24 +1815,32 @@ void launch_upsample_filled(int dim, const int32_t* prev, int32_t* image, int si
 
 void launch_eval_pixels(const EvalVoxelsArgs& a, const Mat3& mat, int grid, cudaStream_t s) {
     const bool local = use_remap(a.n_slots);
-    const int fw = float_warps(a.n_slots);
-    const size_t smem = walk_smem(a.n_rows, local, fw);
+    const int G = a.group;
+    const int fw = float_warps(a.n_slots, G);
+    const size_t smem = walk_smem(a.n_rows, local, fw, G);
     if (a.heat) {
         if (local) k_eval_pixels<true, true><<<grid, fw * 32, smem, s>>>(a, mat);
         else k_eval_pixels<false, true><<<grid, fw * 32, smem, s>>>(a, mat);
     } else if (local) k_eval_pixels<true><<<grid, fw * 32, smem, s>>>(a, mat);
-    else k_eval_pixels<false><<<grid, fw * 32, smem, s>>>(a, mat);
+    else pick_float(G, float_unroll(), [&](auto g, auto u) {
+        k_eval_pixels<false, false, decltype(g)::value, decltype(u)::value><<<grid, fw * 32, smem, s>>>(a, mat);
+        return 0;
+    });
 }
 
 void launch_eval_voxels(const EvalVoxelsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
     const bool local = use_remap(a.n_slots);
-    const int fw = float_warps(a.n_slots);
-    const size_t smem = walk_smem(a.n_rows, local, fw);
+    const int G = a.group;
+    const int fw = float_warps(a.n_slots, G);
+    const size_t smem = walk_smem(a.n_rows, local, fw, G);
     if (a.heat) {
         if (local) k_eval_voxels<true, true><<<grid, fw * 32, smem, s>>>(a, mat);
         else k_eval_voxels<false, true><<<grid, fw * 32, smem, s>>>(a, mat);
     } else if (local) k_eval_voxels<true><<<grid, fw * 32, smem, s>>>(a, mat);
-    else k_eval_voxels<false><<<grid, fw * 32, smem, s>>>(a, mat);
+    else pick_float(G, float_unroll(), [&](auto g, auto u) {
+        k_eval_voxels<false, false, decltype(g)::value, decltype(u)::value><<<grid, fw * 32, smem, s>>>(a, mat);
+        return 0;
+    });
 }
 
 void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
@@ -1626,8 +1850,9 @@ void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_
     else k_normals<false><<<grid, kEvalThreads, smem, s>>>(a, mat);
 }
 
-void launch_preload_tiles(TileNode* tiles, int32_t count, int32_t* n_tiles, int grid, cudaStream_t s) {
-    k_preload_tiles<<<grid, 256, 0, s>>>(tiles, count, n_tiles);
+void launch_preload_tiles(TileNode* tiles, int32_t* items, int32_t count, int32_t* n_tiles, int32_t* n_items, int grid,
+                          cudaStream_t s) {
+    k_preload_tiles<<<grid, 256, 0, s>>>(tiles, items, count, n_tiles, n_items);
 }
 
 void launch_heat_finish(const unsigned long long* units, float* heat, long long n, int32_t n_clauses, int grid,
@@ -1657,12 +1882,20 @@ int occupancy_eval_tiles(int dim, bool root, int n_slots) {
     return local ? occ(k_eval_tiles<2, false, true>, smem) : occ(k_eval_tiles<2, false, false>, smem);
 }
 
-int occupancy_eval_voxels(int dim, int n_slots) {
+int occupancy_eval_voxels(int dim, int n_slots, int group) {
     const bool local = use_remap(n_slots);
-    const int fw = float_warps(n_slots);
-    const size_t smem = walk_smem(walk_rows(n_slots), local, fw);
-    if (dim == 3) return local ? occ(k_eval_voxels<true>, smem, fw * 32) : occ(k_eval_voxels<false>, smem, fw * 32);
-    return local ? occ(k_eval_pixels<true>, smem, fw * 32) : occ(k_eval_pixels<false>, smem, fw * 32);
+    const int fw = float_warps(n_slots, group);
+    const size_t smem = walk_smem(walk_rows(n_slots), local, fw, group);
+    if (dim == 3) {
+        if (local) return occ(k_eval_voxels<true>, smem, fw * 32);
+        return pick_float(group, float_unroll(), [&](auto g, auto u) {
+            return occ(k_eval_voxels<false, false, decltype(g)::value, decltype(u)::value>, smem, fw * 32);
+        });
+    }
+    if (local) return occ(k_eval_pixels<true>, smem, fw * 32);
+    return pick_float(group, float_unroll(), [&](auto g, auto u) {
+        return occ(k_eval_pixels<false, false, decltype(g)::value, decltype(u)::value>, smem, fw * 32);
+    });
 }
 
 int occupancy_normals(int n_slots) {

@@ -89,7 +89,10 @@ struct RankArgs {
     const int32_t* image;     // this level's filled image
     int32_t* n_active;        // out: survivors
     int32_t* active_list;     // out: rank -> tile index (not at the last level)
-    TileNode* out_tiles;      // out: compact survivor list (last level only)
+    TileNode* out_tiles;      // out: compact survivor list (last level only), tiles sharing a tape adjacent
+    int32_t* items;           // out: float-pass work items, start * 8 + count (last level only)
+    int32_t* n_items;         // out: how many
+    int32_t gmax;             // tiles per work item (float_group)
     long long next_cap;       // capacity (tiles) of the stage that receives survivors
     int32_t last_level;
     int32_t level;
@@ -101,7 +104,9 @@ struct EvalVoxelsArgs {
     int32_t* image;           // full-resolution image / heightmap
     const TileNode* tiles;    // compact survivor list of the last interval level
     int32_t tiles_cap;
-    const int32_t* n_tiles;
+    const int32_t* items;     // work items: runs of up to `group` tiles sharing a tape (start * 8 + count)
+    const int32_t* n_items;
+    int32_t group;            // tiles per work item: 1, 2 or 4 (float_group)
     uint32_t tps;             // survivor-level tiles per side (size/4 or size/8)
     FrameCtl* ctl;
     int32_t* queue;
@@ -128,7 +133,8 @@ struct NormalsArgs {
 };
 
 void init_kernels(int max_smem_optin);
-void launch_preload_tiles(TileNode* tiles, int32_t count, int32_t* n_tiles, int grid, cudaStream_t s);
+void launch_preload_tiles(TileNode* tiles, int32_t* items, int32_t count, int32_t* n_tiles, int32_t* n_items, int grid,
+                          cudaStream_t s);
 void launch_heat_finish(const unsigned long long* units, float* heat, long long n, int32_t n_clauses, int grid,
                         cudaStream_t s);
 void launch_begin_frame(FrameCtl* ctl, int32_t first_free, cudaStream_t s);
@@ -142,9 +148,10 @@ void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_
 
 // Resident CTAs per SM for a given slot count (sizes the persistent grids).
 int walk_rows(int n_slots);
-int float_warps(int n_slots);
+int float_group(int n_slots, bool heat);
+int float_warps(int n_slots, int group);
 int occupancy_eval_tiles(int dim, bool root, int n_slots);
-int occupancy_eval_voxels(int dim, int n_slots);
+int occupancy_eval_voxels(int dim, int n_slots, int group);
 int occupancy_normals(int n_slots);
 
 }  // namespace mprb

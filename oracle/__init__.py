@@ -97,6 +97,26 @@ def view_matrix_3d():
     return t
 
 
+HEIGHTMAP_SO = _DIR / "_build" / "libheightmap_cpu.so"
+_heightmap = None
+
+
+def heightmap_cpu_ms(cells, dim: int, size: int, threads: int = 8, depth_out=None) -> float:
+    """One frame of the libfive-algorithm CPU renderer (the stand-in the reference drivers link,
+    oracle/heightmap_cabi.cpp) on `threads` host threads; returns its milliseconds."""
+    global _heightmap
+    if _heightmap is None:
+        if not HEIGHTMAP_SO.exists():
+            subprocess.run(["make", "-C", str(_DIR), "_build/libheightmap_cpu.so"], check=True, capture_output=True)
+        L = C.CDLL(str(HEIGHTMAP_SO))
+        L.mpro_heightmap_ms.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.mpro_heightmap_ms.restype = C.c_double
+        _heightmap = L
+    cells = np.ascontiguousarray(cells, dtype=np.uint64)
+    ptr = depth_out.ctypes.data if depth_out is not None else None
+    return float(_heightmap.mpro_heightmap_ms(cells.ctypes.data, cells.size, dim, size, threads, ptr))
+
+
 def tape_hashes(arena: np.ndarray, starts: np.ndarray):
     """Hash + length of the logical tape starting at each arena index."""
     L = oracle_lib()
@@ -244,6 +264,16 @@ def ref_lib():
         L.ref_render2d_brute.argtypes = [vp, vp, vp, C.c_float]
         L.ref_render2d_heatmap.argtypes = [vp, vp, vp, C.c_float, vp]
         L.ref_render3d_heatmap.argtypes = [vp, vp, vp, vp]
+        if hasattr(L, "ref_effects_create"):          # libraries built before effects.cu joined the recipe lack these
+            L.ref_effects_create.restype = vp
+            L.ref_effects_destroy.argtypes = [vp]
+            L.ref_effects_samples.argtypes = [vp, vp, vp]
+            L.ref_effects_draw_ssao.argtypes = [vp, vp]
+            L.ref_effects_draw_shaded.argtypes = [vp, vp]
+            L.ref_effects_image.argtypes = [vp]
+            L.ref_effects_image.restype = vp
+            L.ref_effects_tmp.argtypes = [vp]
+            L.ref_effects_tmp.restype = vp
         _ref = L
     return _ref
 
@@ -342,6 +372,41 @@ class RefGpu(_Base):
     def _normals_ptr(self): return self.L.ref_normals(self.h)
     def _arena_ptr(self): return self.L.ref_tape_data(self.h)
     def tape_index(self): return int(self.L.ref_tape_index(self.h))
+
+
+class RefEffects:
+    """The unmodified reference mpr::Effects (src/effects.cu compiled into oracle/_ref against the
+    Eigen stand-in in oracle/shim).  GPU box only."""
+
+    def __init__(self):
+        self.L = ref_lib()
+        if not hasattr(self.L, "ref_effects_create"):
+            raise RuntimeError("oracle/_ref was built without src/effects.cu; run `make -C oracle ref`")
+        self.h = self.L.ref_effects_create()
+
+    def samples(self):
+        """(kernel 64x3, rvecs 256x3) as Fortran-ordered float32 - the constructor's rand() draws."""
+        k = np.zeros((64, 3), dtype=np.float32, order="F")
+        r = np.zeros((256, 3), dtype=np.float32, order="F")
+        self.L.ref_effects_samples(self.h, k.ctypes.data, r.ctypes.data)
+        return k, r
+
+    def draw(self, ctx: "RefGpu", shaded=False):
+        (self.L.ref_effects_draw_shaded if shaded else self.L.ref_effects_draw_ssao)(self.h, ctx.h)
+        s = ctx.size
+        return (_as_array(self.L.ref_effects_image(self.h), (s, s), np.int32).copy(),
+                _as_array(self.L.ref_effects_tmp(self.h), (s, s), np.int32).copy())
+
+    def close(self):
+        if self.h:
+            self.L.ref_effects_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def effects(depth, normals, kernel, rvecs, shaded=False):

@@ -16,6 +16,7 @@
 #include <cstring>
 
 #include "context.hpp"
+#include "effects.hpp"
 #include "parameters.hpp"
 #include "tape.hpp"
 
@@ -105,5 +106,23 @@ void ref_download(void* c, int32_t* image_out, uint32_t* normals_out) {
     if (image_out) cudaMemcpy(image_out, ctx->stages[3].filled.get(), n * sizeof(int32_t), cudaMemcpyDeviceToHost);
     if (normals_out) cudaMemcpy(normals_out, ctx->normals.get(), n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
 }
+
+// ---- mpr::Effects (src/effects.cu), compiled unmodified against oracle/shim/Eigen ----------------
+// The sample sets are protected members filled from rand() by the constructor; a derived type
+// exposes them so that the product can be handed the very same numbers.
+struct RefEffects : mpr::Effects {
+    const float* kernel() const { return ssao_kernel.data(); }       // 64 x 3, column major
+    const float* rvecs() const { return ssao_rvecs.data(); }         // 256 x 3, column major
+};
+void* ref_effects_create(void) { return new RefEffects(); }
+void ref_effects_destroy(void* fx) { delete static_cast<RefEffects*>(fx); }
+void ref_effects_samples(void* fx, float* kernel_64x3, float* rvecs_256x3) {
+    memcpy(kernel_64x3, static_cast<RefEffects*>(fx)->kernel(), sizeof(float) * 64 * 3);
+    memcpy(rvecs_256x3, static_cast<RefEffects*>(fx)->rvecs(), sizeof(float) * 256 * 3);
+}
+void ref_effects_draw_ssao(void* fx, void* c) { static_cast<RefEffects*>(fx)->drawSSAO(*static_cast<mpr::Context*>(c)); }
+void ref_effects_draw_shaded(void* fx, void* c) { static_cast<RefEffects*>(fx)->drawShaded(*static_cast<mpr::Context*>(c)); }
+int32_t* ref_effects_image(void* fx) { return static_cast<RefEffects*>(fx)->image.get(); }
+int32_t* ref_effects_tmp(void* fx) { return static_cast<RefEffects*>(fx)->tmp.get(); }
 
 }  // extern "C"

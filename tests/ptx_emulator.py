@@ -304,6 +304,41 @@ class LoopMachine(Machine):
                 addr = self.val(m.group(1))
                 self.smem[addr] = self.val(m.group(2))
                 self.smem[addr + 4] = self.val(m.group(3))
+            elif op in ("ld.shared.b64", "ld.shared.v2.b64", "st.shared.b64", "st.shared.v2.b64"):
+                # 64-bit registers hold two f32 patterns (lo | hi << 32): the float loop's sample pairs
+                am = re.search(r"\[(\w+|%\d+)(?:\+(\d+))?\]", ins)
+                addr = self.val(am.group(1)) + int(am.group(2) or 0)
+                names = [x.strip() for x in re.sub(r"\[.*?\]", "", ins.split(None, 1)[1]).replace("{", "").replace("}", "").split(",") if x.strip()]
+                for k, name in enumerate(names):
+                    if op.startswith("ld"):
+                        self.set(name, self.smem.get(addr + 8 * k, 0) | (self.smem.get(addr + 8 * k + 4, 0) << 32))
+                    else:
+                        v = self.r[name]
+                        self.smem[addr + 8 * k] = v & 0xffffffff
+                        self.smem[addr + 8 * k + 4] = v >> 32
+            elif op == "mov.b64":
+                body = ins.split(None, 1)[1]
+                um = re.fullmatch(r"\{(\w+),\s*(\w+)\}\s*,\s*(\w+)", body.strip())
+                pm2 = re.fullmatch(r"(\w+)\s*,\s*\{(\w+),\s*(\w+)\}", body.strip())
+                if um:                                       # unpack
+                    v = self.r[um.group(3)]
+                    self.set(um.group(1), v & 0xffffffff)
+                    self.set(um.group(2), v >> 32)
+                elif pm2:                                    # pack
+                    self.set(pm2.group(1), self.val(pm2.group(2)) | (self.val(pm2.group(3)) << 32))
+                else:
+                    d, src = [x.strip() for x in body.split(",")]
+                    self.set(d, 0 if src == "0" else self.r[src])
+            elif re.fullmatch(r"(add|sub|mul)\.rn\.f32x2", op):
+                d, x, y = [t.strip() for t in ins.split(None, 1)[1].split(",")]
+                kind = op.split(".")[0]
+                out = 0
+                for half in (0, 32):
+                    xa, yb = b2f((self.r[x] >> half) & 0xffffffff), b2f((self.r[y] >> half) & 0xffffffff)
+                    if kind == "sub":
+                        yb = np.float32(-yb) if not np.isnan(yb) else yb
+                    out |= f2b({"add": fadd, "sub": fadd, "mul": fmul}[kind](xa, yb, "rn")) << half
+                self.set(d, out)
             elif op == "prmt.b32":
                 a = [x.strip() for x in ins.split(None, 1)[1].split(",")]
                 src = (self.val(a[2]) << 32) | self.val(a[1])

@@ -270,6 +270,34 @@ def test_effects_match_cpu_restatement(model, size):
     ctx.close()
 
 
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("model,size", [("bear", 256), ("architecture", 512), ("bear", 1024)])
+def test_effects_match_reference_build(model, size):
+    """mpr::Effects::drawSSAO / drawShaded against the reference's own src/effects.cu, compiled unmodified
+    into oracle/_ref (with the Eigen stand-in of oracle/shim for its small-vector algebra), on the same
+    frame and the same sample sets: bit for bit, both result buffers."""
+    cells = load_tape(model)
+    ref = oracle.RefGpu(size)
+    ref.render3D(cells)
+    rfx = oracle.RefEffects()
+    kernel, rvecs = rfx.samples()
+    ctx, tape = render(model, 3, size)
+    assert np.array_equal(ctx.image(), ref.image()) and np.array_equal(ctx.normals(), ref.normals())
+    fx = capi.Effects(kernel, rvecs)
+    for shaded in (False, True):
+        want_image, want_tmp = rfx.draw(ref, shaded=shaded)
+        (fx.drawShaded if shaded else fx.drawSSAO)(ctx)
+        got_image, got_tmp = fx.image().copy(), fx.tmp().copy()
+        for name, got, want in (("image", got_image, want_image), ("tmp", got_tmp, want_tmp)):
+            bad = int((got != want).sum())
+            assert bad == 0, (model, size, "shaded" if shaded else "ssao", name, bad,
+                              np.argwhere(got != want)[:4].tolist())
+    fx.close()
+    rfx.close()
+    ctx.close()
+    ref.close()
+
+
 @pytest.mark.parametrize("model,size", [("hello_world", 256), ("prospero", 512)])
 def test_brute_force_frame(model, size):
     """Context::render2D_brute (context.cu:1461-1508): same image as the subdivided frame, as the

@@ -467,8 +467,10 @@ def test_generated_interval_loop_runs_whole_tapes_like_the_c_restatement():
         assert (m.r["cw"], m.r["n"], m.r["any"] != 0) == (cw, cnt, anyc != 0)
 
 
-def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation():
-    """Same for the float pass's loop (two samples per lane), against numpy float32 arithmetic with the
+@pytest.mark.parametrize("G,inc", [(1, "float_loop_ptx.inc"), (2, "float_loop_ptx_g2.inc"), (4, "float_loop_ptx_g4.inc")])
+def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation(G, inc):
+    """Same for the float pass's loops (G tiles per warp, two samples per tile and lane; slot bytes
+    pre-multiplied by G as annotate_chunk does), against numpy float32 arithmetic with the
     clause semantics of eval_voxels_f (reference context.cu:887-920).  exp / log are left out: their
     handlers are libdevice's PTX (ex2.approx), which the interpreter does not model."""
     import importlib.util
@@ -476,7 +478,7 @@ def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation():
     spec = importlib.util.spec_from_file_location("gen_float_loop", ROOT / "tools" / "gen_float_loop.py")
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    asm = load_asm(ROOT / "mpr_b200" / "csrc" / "float_loop_ptx.inc")
+    asm = load_asm(ROOT / "mpr_b200" / "csrc" / inc)
     ops = [o for o in sorted(mod.OPS) if o not in (10, 12)]
     rng = np.random.default_rng(5)
     CH, SB = 0x1000, 0x4000
@@ -491,7 +493,7 @@ def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation():
                     24: lambda: l / imm, 25: lambda: imm / r, 26: lambda: l / r,
                     27: lambda: imm, 28: lambda: l, 29: lambda: r}[op]()
 
-    for trial in range(40):
+    for trial in range(40 if G == 1 else 15):
         n = int(rng.integers(5, 40))
         cells = []
         for _ in range(n):
@@ -503,17 +505,20 @@ def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation():
         noted = _mini_annotate(cells, mod)
         smem = {}
         for j, c in enumerate(noted):
-            smem[CH + 8 * j], smem[CH + 8 * j + 4] = c & 0xffffffff, c >> 32
-        slots = {s: rng.normal(0, 2, 2).astype(f32) for s in range(7)}
+            w = c & 0xffffffff
+            w = (w & 0xff) | (((w >> 8) * G) << 8)          # slot ids -> row offsets in 256-byte units
+            smem[CH + 8 * j], smem[CH + 8 * j + 4] = w, c >> 32
+        slots = {s: rng.normal(0, 2, 2 * G).astype(f32) for s in range(7)}
         for s, v in slots.items():
-            smem[SB + 256 * s], smem[SB + 256 * s + 4] = f2b(v[0]), f2b(v[1])
+            for k in range(2 * G):
+                smem[SB + 256 * G * s + 4 * k] = f2b(v[k])
         m = LoopMachine(asm, {"cp": CH - 8, "sb": SB, "w": 0, "imm": 0},
                         {"%0": "cp", "%1": "w", "%2": "imm", "%3": "sb"}, smem).execute()
         assert m.r["cp"] == CH + 8 * n and (m.r["w"] & 0xff) == 0
         for c in cells[:-1]:
             op, out, lhs, rhs = c & 0xff, (c >> 8) & 0xff, (c >> 16) & 0xff, (c >> 24) & 0xff
             imm = b2f(c >> 32)
-            slots[out] = np.array([clause(op, slots[lhs][k], slots[rhs][k], imm) for k in range(2)], dtype=f32)
+            slots[out] = np.array([clause(op, slots[lhs][k], slots[rhs][k], imm) for k in range(2 * G)], dtype=f32)
         for s, v in slots.items():
-            got = np.array([b2f(smem[SB + 256 * s]), b2f(smem[SB + 256 * s + 4])], dtype=f32)
+            got = np.array([b2f(smem[SB + 256 * G * s + 4 * k]) for k in range(2 * G)], dtype=f32)
             assert ((got == v) | (np.isnan(got) & np.isnan(v))).all(), (trial, s, got, v)
