@@ -282,9 +282,10 @@ def run_mine(args, workloads):
             else:
                 ctx.render3D_host(job["cells"], None, None)
             gather(job)
-            job["out_img"].copy_(job["dev_img"])
-            if job["dim"] == 3:
-                job["out_nrm"].copy_(job["dev_nrm"])
+            if rank == 0:           # the caller's device holds the frame; it alone hands it to the host
+                job["out_img"].copy_(job["dev_img"])
+                if job["dim"] == 3:
+                    job["out_nrm"].copy_(job["dev_nrm"])
             torch.cuda.synchronize()
         return (time.perf_counter() - t0) * 1e3
 

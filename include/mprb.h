@@ -30,7 +30,10 @@ extern "C" {
 #define MPRB_OK 0
 #define MPRB_E_CUDA 1        /* a CUDA runtime call failed */
 #define MPRB_E_ARG 2         /* invalid argument */
-#define MPRB_E_OVERFLOW 3    /* a tile list outgrew its (worst-case-capped) array */
+#define MPRB_E_OVERFLOW 3    /* a tile list outgrew its array: every level's list is allocated once for the
+                                worst case (64 children per surviving parent) but capped at 64 Mi tiles
+                                (805 MB); beyond that the frame is incomplete (mprb_frame_stats.overflow
+                                names the level) and the context stays usable */
 #define MPRB_E_PARSE 4       /* malformed .frep input */
 
 typedef struct mprb_ctx mprb_ctx;

@@ -143,6 +143,9 @@ struct mprb_ctx {
     // multi-GPU: sub-contexts on the other devices (owned by this, the primary, context)
     std::vector<mprb_ctx*> peers;
     cudaEvent_t ev_body = nullptr;   // the frame's kernels are enqueued up to here (no timing)
+    // exchange helpers may run on a caller's stream: the next frame waits for them
+    cudaEvent_t ev_ext = nullptr;
+    bool ext_pending = false;
 };
 
 namespace {
@@ -373,6 +376,10 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
     else memcpy(m3.d, matrix, sizeof(m3.d));
     const void* mat = dim == 3 ? static_cast<const void*>(&m4) : static_cast<const void*>(&m3);
 
+    if (c->ext_pending) {            // an exchange helper touched the frame buffers on another stream
+        MPRB_CUDA(cudaStreamWaitEvent(s, c->ev_ext, 0));
+        c->ext_pending = false;
+    }
     cudaEventRecord(c->ev_begin, s);
     Timer tm{c};
     tm.mark();
@@ -521,6 +528,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
     {
         EvalVoxelsArgs va = {};
         va.arena = c->arena;
+        va.arena_cap = int32_t(c->arena_cells);
         va.image = c->filled[3];
         va.tiles = c->tiles[3];
         va.tiles_cap = int32_t(std::min<long long>(c->tiles_cap[3], INT32_MAX));
@@ -810,6 +818,7 @@ static int create_one(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx
     cudaEventCreate(&c->ev_begin);
     cudaEventCreate(&c->ev_end);
     cudaEventCreateWithFlags(&c->ev_body, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_ext, cudaEventDisableTiming);
     for (auto& ev : c->ev_k) cudaEventCreate(&ev);
 
     // Filled images: (S/64)^2, (S/16)^2, (S/4)^2, S^2 (context.cpp:21-26)
@@ -890,6 +899,7 @@ void mprb_ctx_destroy(mprb_ctx* c) {
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     if (c->ev_body) cudaEventDestroy(c->ev_body);
+    if (c->ev_ext) cudaEventDestroy(c->ev_ext);
     for (auto& ev : c->ev_k) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1063,6 +1073,8 @@ static int exchange_check(const mprb_ctx* c, int dim) {
     const int tiles = c->size / 64;
     if (c->row_mod <= 1 || c->row_begin != 0 || c->row_end != tiles || tiles % c->row_mod != 0)
         return fail(MPRB_E_ARG, "exchange needs row_mod = world > 1 over the whole frame, tiles per side divisible by world");
+    if (dim == 3 && c->size > 32768)
+        return fail(MPRB_E_ARG, "exchange carries depth as int16: image side must not exceed 32768");
     return MPRB_OK;
 }
 
@@ -1078,6 +1090,10 @@ int mprb_exchange_pack(mprb_ctx* c, int dim, void* dst, void* stream) {
     launch_exchange(true, c->size, c->row_mod, c->row_rem, c->col_step, dim, c->filled[3], c->normals, dst,
                     stream ? cudaStream_t(stream) : c->stream);
     MPRB_CUDA(cudaGetLastError());
+    if (stream && cudaStream_t(stream) != c->stream) {      // order the next frame after this launch
+        MPRB_CUDA(cudaEventRecord(c->ev_ext, cudaStream_t(stream)));
+        c->ext_pending = true;
+    }
     return MPRB_OK;
 }
 
@@ -1088,6 +1104,10 @@ int mprb_exchange_unpack(mprb_ctx* c, int dim, const void* src, void* stream) {
     launch_exchange(false, c->size, c->row_mod, c->row_rem, c->col_step, dim, c->filled[3], c->normals,
                     const_cast<void*>(src), stream ? cudaStream_t(stream) : c->stream);
     MPRB_CUDA(cudaGetLastError());
+    if (stream && cudaStream_t(stream) != c->stream) {      // order the next frame after this launch
+        MPRB_CUDA(cudaEventRecord(c->ev_ext, cudaStream_t(stream)));
+        c->ext_pending = true;
+    }
     return MPRB_OK;
 }
 

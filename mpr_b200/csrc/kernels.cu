@@ -266,7 +266,7 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
     const int warp = threadIdx.x >> 5;
     typedef TapeStream<REMAP> Stream;
     Stream ts;
-    ts.init(s_dyn + warp * Stream::stride(), a.arena);
+    ts.init(s_dyn + warp * Stream::stride(), a.arena, a.arena_cap);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
     Slots2<REMAP> slots;
     slots.base = smem_addr(s_dyn + kEvalWarps * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
@@ -672,6 +672,7 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
             a.tiles[tile_index].next = -1;
         }
     }
+    ts.drain();
     if (lane == 0 && st_tiles) {
         atomicAdd(&a.ctl->stats[ST_I_TILES + a.level], st_tiles);
         atomicAdd(&a.ctl->stats[ST_I_CELLS + a.level], st_cells);
@@ -1216,7 +1217,7 @@ __device__ __forceinline__ float2 float_clause_libdevice(uint32_t op, float2 L)
 // tile g's result pair.  Slot rows are 32 lanes x 8 G bytes: `sb` is this lane's address in row 0
 // and tile g sits 8 g bytes further.
 template <bool REMAP, int G, int U>
-__device__ __forceinline__ void walk_float(TapeStream<REMAP>& ts, int tape, Slots2<REMAP>& slots, unsigned& cells,
+__device__ __forceinline__ void walk_float(TapeStream<REMAP, REMAP>& ts, int tape, Slots2<REMAP>& slots, unsigned& cells,
                                            float2 (&r)[G])
 {
     constexpr int SHIFT = G == 4 ? 2 : (G == 2 ? 1 : 0);
@@ -1279,9 +1280,9 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
     extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = lane_id();
     const int warp = __shfl_sync(kFull, int(threadIdx.x >> 5), 0);   // via shuffle: provably warp-uniform for ptxas
-    typedef TapeStream<REMAP> Stream;
+    typedef TapeStream<REMAP, REMAP> Stream;   // look-ahead only where slots are renamed (see tape_stream.cuh)
     Stream ts;
-    ts.init(s_dyn + warp * Stream::stride(), a.arena);
+    ts.init(s_dyn + warp * Stream::stride(), a.arena, a.arena_cap);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
     Slots2<REMAP> slots;
     slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * G) * 8;
@@ -1345,6 +1346,7 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
         st_tiles += count;
         st_cells += (unsigned long long)cells * count;
     }
+    ts.drain();
     if (lane == 0 && st_tiles) {
         atomicAdd(&a.ctl->stats[ST_F_TILES], st_tiles);
         atomicAdd(&a.ctl->stats[ST_F_CELLS], st_cells);
@@ -1363,9 +1365,9 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
     extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = lane_id();
     const int warp = __shfl_sync(kFull, int(threadIdx.x >> 5), 0);   // via shuffle: provably warp-uniform for ptxas
-    typedef TapeStream<REMAP> Stream;
+    typedef TapeStream<REMAP, REMAP> Stream;   // look-ahead only where slots are renamed (see tape_stream.cuh)
     Stream ts;
-    ts.init(s_dyn + warp * Stream::stride(), a.arena);
+    ts.init(s_dyn + warp * Stream::stride(), a.arena, a.arena_cap);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
     Slots2<REMAP> slots;
     slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * G) * 8;
@@ -1445,6 +1447,7 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
         st_tiles += count;
         st_cells += (unsigned long long)cells * count;
     }
+    ts.drain();
     if (lane == 0 && st_tiles) {
         atomicAdd(&a.ctl->stats[ST_F_TILES], st_tiles);
         atomicAdd(&a.ctl->stats[ST_F_CELLS], st_cells);
@@ -1653,8 +1656,9 @@ __global__ void k_heat_finish(const unsigned long long* __restrict__ units, floa
 // Dynamic shared memory of an interval / float tape-walking CTA: per warp one chunk stream plus
 // 256-byte value rows - one per slot id, or kRemapRows when the stream renames slots.
 bool use_remap(int n_slots);
-static size_t walk_smem(int n_rows, bool remap, int warps = kEvalWarps, int group = 1) {
-    return size_t(warps) * (size_t(n_rows) * 256 * group + (remap ? kStreamStrideRemap : kStreamStridePlain));
+static size_t walk_smem(int n_rows, bool remap, int warps = kEvalWarps, int group = 1, bool float_pass = false) {
+    const int stream = remap ? kStreamStrideRemap : (float_pass ? kStreamStrideSingle : kStreamStridePlain);
+    return size_t(warps) * (size_t(n_rows) * 256 * group + stream);
 }
 // Shared-memory value rows per warp: one per slot id, or a fixed budget when slots are renamed.
 int walk_rows(int n_slots) {
@@ -1684,7 +1688,7 @@ int float_warps(int n_slots, int group) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     }
-    const size_t per_warp = walk_smem(walk_rows(n_slots), use_remap(n_slots), 1, group);
+    const size_t per_warp = walk_smem(walk_rows(n_slots), use_remap(n_slots), 1, group, true);
     int best = 1, best_resident = 0;
     for (int w = 1; w <= kFloatMaxThreads / 32; ++w) {
         int ctas = int(size_t(smem_per_sm) / (w * per_warp + 1024));
@@ -1817,7 +1821,7 @@ void launch_eval_pixels(const EvalVoxelsArgs& a, const Mat3& mat, int grid, cuda
     const bool local = use_remap(a.n_slots);
     const int G = a.group;
     const int fw = float_warps(a.n_slots, G);
-    const size_t smem = walk_smem(a.n_rows, local, fw, G);
+    const size_t smem = walk_smem(a.n_rows, local, fw, G, true);
     if (a.heat) {
         if (local) k_eval_pixels<true, true><<<grid, fw * 32, smem, s>>>(a, mat);
         else k_eval_pixels<false, true><<<grid, fw * 32, smem, s>>>(a, mat);
@@ -1832,7 +1836,7 @@ void launch_eval_voxels(const EvalVoxelsArgs& a, const Mat4& mat, int grid, cuda
     const bool local = use_remap(a.n_slots);
     const int G = a.group;
     const int fw = float_warps(a.n_slots, G);
-    const size_t smem = walk_smem(a.n_rows, local, fw, G);
+    const size_t smem = walk_smem(a.n_rows, local, fw, G, true);
     if (a.heat) {
         if (local) k_eval_voxels<true, true><<<grid, fw * 32, smem, s>>>(a, mat);
         else k_eval_voxels<false, true><<<grid, fw * 32, smem, s>>>(a, mat);
@@ -1885,7 +1889,7 @@ int occupancy_eval_tiles(int dim, bool root, int n_slots) {
 int occupancy_eval_voxels(int dim, int n_slots, int group) {
     const bool local = use_remap(n_slots);
     const int fw = float_warps(n_slots, group);
-    const size_t smem = walk_smem(walk_rows(n_slots), local, fw, group);
+    const size_t smem = walk_smem(walk_rows(n_slots), local, fw, group, true);
     if (dim == 3) {
         if (local) return occ(k_eval_voxels<true>, smem, fw * 32);
         return pick_float(group, float_unroll(), [&](auto g, auto u) {

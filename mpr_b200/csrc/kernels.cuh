@@ -101,6 +101,7 @@ struct RankArgs {
 
 struct EvalVoxelsArgs {
     const uint64_t* arena;
+    int32_t arena_cap;        // arena size in cells
     int32_t* image;           // full-resolution image / heightmap
     const TileNode* tiles;    // compact survivor list of the last interval level
     int32_t tiles_cap;

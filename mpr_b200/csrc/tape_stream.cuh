@@ -42,8 +42,11 @@ namespace mprb {
 
 constexpr int kRemapRowsDefault = 16;           // shared-memory value rows per warp in REMAP mode
 constexpr int kRemapRowsMin = 8;                //   (MPRB_REMAP_ROWS overrides; rows beyond spill to local memory)
-constexpr int kStreamStridePlain = 640;         // raw chunk 512 + mbarrier, padded to 128
-constexpr int kStreamStrideRemap = 1408;        // + renamed chunk 512 + table 256
+// Multiples of 128 bytes: the value rows that follow the streams in shared memory are 256-byte lines
+// read by a whole warp, and a misaligned line costs a third wavefront per access.
+constexpr int kStreamStridePlain = 1152;        // two raw chunks 2 x 512 + two mbarriers, padded
+constexpr int kStreamStrideRemap = 1920;        // + renamed chunk 512 + table 256, padded
+constexpr int kStreamStrideSingle = 640;        // AHEAD = false: one raw chunk 512 + mbarrier, padded
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -73,31 +76,46 @@ __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-template <bool REMAP>
+// AHEAD = false drops the second raw buffer and the look-ahead: where shared memory per warp decides how
+// many warps an SM holds (the float pass without renaming: ~6 KB of value rows per warp) the extra 512
+// bytes cost more than the hidden copy latency returns (measured, bear 1024^3: 4.74 vs 4.98 ms).
+template <bool REMAP, bool AHEAD = true>
 struct TapeStream {
-    uint32_t buf;            // shared-space address of the raw 64-cell chunk
+    uint32_t buf;            // shared-space address of the raw 64-cell chunk being walked
+    uint32_t other;          // the second raw buffer: the chunk the walk will jump to next is loaded here ahead of time
     uint32_t rd;             // buffer the walkers read: renamed copy (REMAP) or the raw chunk
-    uint32_t bar;            // mbarrier
+    uint32_t bars;           // two mbarriers, one per raw buffer: bars + 8 * (buffer index)
+    uint32_t lo;             // address of raw buffer 0 (buffer index = (addr - lo) >> 9)
     uint32_t table;          // REMAP: slot id -> row, 256 bytes, 0xFF = not seen yet
-    uint32_t phase;
+    uint32_t parity;         // bit k: phase parity the next wait on buffer k has to see
     uint32_t next_row;       // REMAP: rows handed out so far for the current tape
-    int base;                // arena index of buffer cell 0 (multiple of 64), or -1
+    int base;                // arena index of cell 0 of `buf` (multiple of 64), or -1
+    int pre_base;            // arena index of the chunk requested into `other`, or -1 (a request is always waited
+                             // for before its buffer or barrier is used again)
+    int cap;                 // arena size in cells (look-ahead targets are checked against it)
     const uint64_t* arena;
 
-    static __host__ __device__ constexpr int stride() { return REMAP ? kStreamStrideRemap : kStreamStridePlain; }
+    static __host__ __device__ constexpr int stride() {
+        return REMAP ? kStreamStrideRemap : (AHEAD ? kStreamStridePlain : kStreamStrideSingle);
+    }
 
     // storage: stride() bytes of shared memory owned by this warp, 128-byte aligned
-    __device__ __forceinline__ void init(void* storage, const uint64_t* arena_) {
-        buf = smem_addr(storage);
-        bar = buf + kChunk * 8;
-        rd = REMAP ? buf + 640 : buf;
-        table = buf + 640 + 512;
-        phase = 0;
+    __device__ __forceinline__ void init(void* storage, const uint64_t* arena_, int arena_cells) {
+        lo = smem_addr(storage);
+        buf = lo;
+        other = lo + kChunk * 8;
+        bars = lo + (AHEAD ? 2 : 1) * kChunk * 8;
+        rd = REMAP ? bars + 16 : buf;
+        table = bars + 16 + 512;
+        parity = 0;
         next_row = 0;
         base = -1;
+        pre_base = -1;
+        cap = arena_cells;
         arena = arena_;
         if ((threadIdx.x & 31) == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars) : "memory");
+            if (AHEAD) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -133,37 +151,84 @@ struct TapeStream {
         }
         if (lane == 0) sts_u8(table, 0);
         next_row = row;
-        base = -1;                      // the renamed copy of a resident chunk belongs to the old tape
+        // the renamed copy of a resident chunk belongs to the old tape: forget the chunk (a raw
+        // chunk that is already on its way stays valid - renaming happens when it becomes current)
+        release();
         __syncwarp();
         return out;
     }
 
-    __device__ __forceinline__ void load_chunk(int want) {
-        // Without renaming the walkers annotate the raw chunk in place (generic-proxy byte stores,
-        // kernels.cu:annotate_chunk); the bulk copy below writes the same bytes through the async
-        // proxy, so those stores are ordered before it explicitly.
-        if (!REMAP) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();                                   // everyone is done reading the old chunk
+    // Drops the current chunk, handing its buffer over only once nothing is in flight into it.
+    __device__ __forceinline__ void release() { base = -1; }
+
+    // Bulk copy of the chunk at arena cell `want` into raw buffer `dst`; completion is signalled on
+    // that buffer's mbarrier.  The buffers are also written with ordinary stores (the walkers annotate
+    // chunks in place, kernels.cu:annotate_chunk) while the bulk copy writes through the async proxy,
+    // hence the proxy fence.
+    __device__ __forceinline__ void request(uint32_t dst, int want) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();                                   // everyone is done reading what was there
         if ((threadIdx.x & 31) == 0) {
+            const uint32_t bar = bars + (((dst - lo) >> 9) << 3);
             const uint64_t* src = arena + want;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kChunk * 8)
                          : "memory");
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                ::"r"(buf), "l"(src), "r"(kChunk * 8), "r"(bar)
+                ::"r"(dst), "l"(src), "r"(kChunk * 8), "r"(bar)
                 : "memory");
         }
-        // every lane waits on the barrier phase (hardware-suspended try_wait, not a spin on memory)
+    }
+    // Every lane waits for the request into `dst` (hardware-suspended try_wait, not a spin on memory).
+    __device__ __forceinline__ void wait(uint32_t dst) {
+        const uint32_t k = (dst - lo) >> 9;
+        const uint32_t bar = bars + (k << 3);
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
             "WAIT_%=:\n"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
             "@!p bra WAIT_%=;\n"
-            "}\n" ::"r"(bar), "r"(phase)
+            "}\n" ::"r"(bar), "r"((parity >> k) & 1u)
             : "memory");
-        phase ^= 1;
+        parity ^= 1u << k;
+    }
+
+    // Makes the chunk at arena cell `want` current: it is either the one requested ahead of time
+    // (swap buffers) or has to be fetched now.
+    __device__ __forceinline__ void load_chunk(int want) {
+        __syncwarp();                                   // everyone is done reading the old chunk (and its renamed copy)
+        if (want == pre_base) {
+            wait(other);
+            // swap the roles of the two buffers (written as arithmetic on the buffer index, which
+            // ptxas can follow on its uniform datapath; a swap through a temporary it cannot)
+            buf = lo + (lo + kChunk * 8 - buf);
+            other = lo + (lo + kChunk * 8 - buf);
+        } else {
+            if (pre_base >= 0) wait(other);             // an unused look-ahead still owns `other` and its barrier
+            request(buf, want);
+            wait(buf);
+        }
+        pre_base = -1;
+        if (!REMAP) rd = buf;
         base = want;
+    }
+
+    // Look-ahead: the cell at offset `link` of the current chunk (63 walking forward, 0 walking
+    // backward) is a JUMP when the tape goes on in another chunk; request that chunk into the
+    // other buffer now, a whole chunk's worth of clauses before the walk gets there.  (The cell can
+    // be stale data that merely looks like a JUMP - a tape that ends before cell 63 - so the target
+    // is range-checked and a useless request costs one 512-byte read.)
+    __device__ __forceinline__ void look_ahead(int link) {
+        if (!AHEAD) return;
+        const uint2 c = lds_u2(buf + link * 8);
+        // (in-place hints live in bits 5-7 of the opcode byte; a JUMP never carries any.)  Written as one
+        // predicate, not as early returns: with those ptxas stops treating the stream state as
+        // warp-uniform, and the walkers' clause fetch / decode / dispatch fall off the uniform datapath.
+        const int t = (base + link + int32_t(c.y)) & ~(kChunk - 1);
+        const bool go = (c.x & 0xff) == OP_JUMP && t >= 0 && t < cap && t != base;
+        if (go) request(other, t);
+        pre_base = go ? t : -1;
     }
 
     // REMAP: rewrites the raw chunk into the renamed buffer.  Cells in [lo, hi] (hi = the first
@@ -221,6 +286,12 @@ struct TapeStream {
         __syncwarp();
     }
 
+    // Before the CTA retires: no bulk copy may still be on its way into this warp's buffers.
+    __device__ __forceinline__ void drain() {
+        if (pre_base >= 0) wait(other);
+        pre_base = -1;
+    }
+
     // Forward walking: makes the chunk of arena cell `index` resident; the walk continues at
     // index + 1, so cells up to `index` in that chunk are not part of this tape.
     // Returns true when a new chunk was brought in (false: it was already resident).
@@ -228,6 +299,7 @@ struct TapeStream {
         const int want = index & ~(kChunk - 1);
         if (want == base) return false;
         load_chunk(want);
+        look_ahead(kChunk - 1);
         if (REMAP) rename((index & (kChunk - 1)) + 1, true);
         return true;
     }
@@ -238,6 +310,7 @@ struct TapeStream {
         const int want = index & ~(kChunk - 1);
         if (want == base) return;
         load_chunk(want);
+        look_ahead(0);
         if (REMAP) rename(0, false);
     }
 };

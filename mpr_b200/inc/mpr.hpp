@@ -93,6 +93,13 @@ inline constexpr unsigned pow(unsigned p, unsigned n) { return n ? p * pow(p, n 
 
 namespace detail {
 inline void check(int code, const char* what) {      // CUDA_CHECK convention: print and exit
+    if (code == MPRB_E_OVERFLOW) {
+        // A tile list outgrew its array (capped at 64 Mi tiles per level; the reference would have
+        // reallocated).  The frame is incomplete but the context is intact: say so and carry on,
+        // like the reference does when its subtape arena runs out (context.cu:336-347).
+        fprintf(stderr, "Warning: %s: %s\n", what, mprb_last_error());
+        return;
+    }
     if (code != 0) {
         fprintf(stderr, "Error: %s: %s\n", what, mprb_last_error());
         exit(code);
