@@ -204,11 +204,12 @@ def run_mine(args, workloads):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL prints its communicator line (rank / nranks) at INFO level; it goes to stderr so that stdout
-        # stays the one JSON line.
+        # NCCL reports its communicator (rank / nranks) at INFO level.  The log goes to a file per rank so
+        # that stdout stays the one JSON line; rank 0 copies the communicator lines to stderr and into the
+        # JSON line ("nccl") once the group is up.
         os.environ.setdefault("NCCL_DEBUG", os.environ.get("MPRB_NCCL_DEBUG", "INFO"))
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        nccl_log = os.environ.setdefault("NCCL_DEBUG_FILE", f"/tmp/mprb_nccl_{os.getpid()}_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     class DevArray:   # wraps a raw device pointer for torch.as_tensor
@@ -238,6 +239,24 @@ def run_mine(args, workloads):
         jobs.append(job)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
+    nccl_info = None
+    if world > 1:
+        dist.barrier()                        # first collective: the communicator exists after this
+        torch.cuda.synchronize()
+        if rank == 0:
+            import glob
+            import socket
+            lines = []
+            pat = nccl_log.replace("%h", socket.gethostname()).replace("%p", str(os.getpid()))
+            for f in glob.glob(pat) + glob.glob(nccl_log.replace("%h", "*").replace("%p", "*")):
+                try:
+                    lines += [l.strip() for l in open(f, errors="replace") if "nranks" in l or "NCCL version" in l]
+                except OSError:
+                    pass
+            lines = sorted(set(lines))[:8]
+            for l in lines:
+                print(l, file=sys.stderr, flush=True)
+            nccl_info = {"world_size": dist.get_world_size(), "backend": dist.get_backend(), "log_lines": lines}
 
     def gather(job):
         """One all-gather of the band(s); returns device ms (0 on one GPU)."""
@@ -333,6 +352,25 @@ def run_mine(args, workloads):
                 got["normals"] = digest(j["out_nrm"].numpy().view(np.uint32))
             (verified if all(got[k] == want[k] for k in got) else mismatched).append(case)
 
+    # BASELINE.json config 4 ("bear 3D heightmap + normals + SSAO"): mpr::Effects::drawSSAO / drawShaded on the
+    # last 3D frame, host clock around the synchronised calls (the reference's GUI times them the same way,
+    # gui/main.cpp:372-391).  Not part of `value`.
+    effects_ms = {}
+    if rank == 0:
+        for j in jobs:
+            if j["dim"] != 3 or world > 1:
+                continue
+            fx = capi.Effects()
+            for name, fn in (("ssao", fx.drawSSAO), ("shaded", fx.drawShaded)):
+                fn(j["ctx"])
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    fn(j["ctx"])
+                effects_ms[f"{j['model']}_{j['dim']}d_{j['size']}_{name}"] = (time.perf_counter() - t0) * 100.0
+            lit = int((j["out_img"].numpy() != 0).sum())
+            effects_ms[f"{j['model']}_{j['dim']}d_{j['size']}_ssao_algorithmic_bytes"] = lit * (64 * 4 + 12) + j["size"] ** 2 * 8
+            fx.close()
+
     # per-kernel timing + counters on separate frames (events between launches perturb nothing
     # in the timed loops above)
     per_kernel, bytes_by_kernel, frames_k = {}, {}, 3
@@ -400,11 +438,12 @@ def run_mine(args, workloads):
                        "e2e_ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(e2e[:, i].mean()) for i, j in enumerate(jobs)},
                        "exchange_ms_per_frame_rank0": {f"{j['model']}_{j['dim']}d_{j['size']}": round(j.get("gather_ms", 0.0) / max(j.get("gather_n", 1), 1), 4) for j in jobs},
                        "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
-                       "frame_stats": stats_one},
+                       "frame_stats": stats_one, "effects_ms": effects_ms},
             "clocks": clk,
             "e2e": {"value": float(e2e_step.mean() / n_frames), "unit": "ms/frame", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
+            "nccl": nccl_info,
             "frames_verified": (not mismatched) and bool(verified),
             "frames_verified_detail": {"equal_to_reference_build": verified, "no_fixture": unverified, "MISMATCH": mismatched},
             "kernel_ms_per_step": {k: round(v, 4) for k, v in per_kernel.items()},
@@ -477,6 +516,21 @@ def run_reference(args, workloads):
         step(frame_e2e)
     e2e = np.array([step(frame_e2e) for _ in range(args.steps)])
     clk = clocks.stop()
+    effects_ms = {}
+    for j in jobs:                       # config 4: the reference's own Effects on its own frame
+        if j["dim"] != 3:
+            continue
+        try:
+            fx = oracle.RefEffects()
+        except Exception:
+            break
+        for name, shaded in (("ssao", False), ("shaded", True)):
+            fx.draw(j["ref"], shaded=shaded)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                (fx.L.ref_effects_draw_shaded if shaded else fx.L.ref_effects_draw_ssao)(fx.h, j["ref"].h)
+            effects_ms[f"{j['model']}_{j['dim']}d_{j['size']}_{name}"] = (time.perf_counter() - t0) * 100.0
+        fx.close()
     n_frames = len(jobs)
     h2d = sum((64 if j["dim"] == 3 else 36) for j in jobs)
     d2h = sum(j["size"] ** 2 * 4 * (2 if j["dim"] == 3 else 1) for j in jobs)
@@ -496,7 +550,8 @@ def run_reference(args, workloads):
                    "wall_ms_per_frame": {name(j): j["wall_ms"] / args.steps for j in jobs},
                    "ms_per_frame": {name(j): float(dev[:, i].mean()) for i, j in enumerate(jobs)},
                    "e2e_ms_per_frame": {name(j): float(e2e[:, i].mean()) for i, j in enumerate(jobs)},
-                   "e2e_protocol": "Tape resident on the device (built once), result downloaded into pinned host buffers"},
+                   "e2e_protocol": "Tape resident on the device (built once), result downloaded into pinned host buffers",
+                   "effects_ms": effects_ms},
         "clocks": clk,
         "e2e": {"value": float(e2e.sum(1).mean() / n_frames), "unit": "ms/frame", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},

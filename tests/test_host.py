@@ -80,6 +80,27 @@ def _frep(nodes):
     return out + b"\xff\xff"
 
 
+def test_archive_bytes_from_libfives_own_tests_are_read_as_written_there():
+    """Known answers held by the reference: libfive/libfive/test/archive.cpp:47-105 pins the archive
+    byte format with literal strings.  Those exact bytes (packed opcode numbering, as mpr builds
+    libfive: CMakeLists.txt:6-8, opcode.hpp:63-101 - VAR_X 2, VAR_Y 3, OP_MIN 22, OP_MAX 23) go through
+    the .frep reader + tape packer here and must come out as the one-clause tape of min(x, y)."""
+    X, Y, MIN, MAX = 2, 3, 22, 23
+    named = b'T"hi"""' + bytes([X, Y, MIN, 1, 0, 0, 0, 0, 0, 0, 0, 0xFF, 0xFF])                  # "With a name"
+    escaped = b'T"hi""\\"\\\\"' + bytes([X, Y, MIN, 1, 0, 0, 0, 0, 0, 0, 0, 0xFF, 0xFF])       # "String escaping"
+    two = (b'T""""' + bytes([X, Y, MIN, 1, 0, 0, 0, 0, 0, 0, 0, 0xFF, 0xFF]) +                # "Multiple independent trees"
+           b'T""""' + bytes([MAX, 1, 0, 0, 0, 0, 0, 0, 0, 0xFF, 0xFF]))
+    for blob in (named, escaped, two):
+        cells = capi.tape_from_frep(blob)             # the drivers take the archive's first shape
+        assert len(cells) == 3
+        hdr, clause, end = (int(c) for c in cells)
+        sx, sy = (hdr >> 8) & 0xFF, (hdr >> 16) & 0xFF
+        assert hdr & 0xFF == 0 and sx and sy and sx != sy and (hdr >> 24) == 0
+        assert clause & 0xFF == 18                                        # GPU_OP_MIN_LHS_RHS
+        assert ((clause >> 16) & 0xFF, (clause >> 24) & 0xFF) == (sx, sy)  # lhs = x, rhs = y (rhs is stored first)
+        assert end & 0xFF == 0 and (end >> 8) & 0xFF == (clause >> 8) & 0xFF
+
+
 def test_packer_known_answer_circle():
     # max(sqrt(x^2 + y^2) - 1, 0.5 - sqrt(x^2 + y^2)): the default shape of the reference's
     # print_tape_table driver (benchmark/print_tape_table.cpp:29)
