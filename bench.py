@@ -170,8 +170,11 @@ def digest(a: np.ndarray) -> str:
 
 
 # Launch order inside one frame (mpr_b200/csrc/api.cu: render()).
-KERNELS_2D = ["eval_tiles", "rank_tiles", "upsample_filled"] * 2 + ["eval_voxels"]
-KERNELS_3D = ["eval_tiles", "rank_tiles", "upsample_filled"] * 3 + ["eval_voxels", "normals"]
+def kernel_names(dim: int, n_launches: int):
+    """The float pass is one launch, or two (work items on compacted tapes, then the rest)."""
+    head = ["eval_tiles", "rank_tiles", "upsample_filled"] * (3 if dim == 3 else 2)
+    tail = ["normals"] if dim == 3 else []
+    return head + ["eval_voxels"] * max(n_launches - len(head) - len(tail), 1) + tail
 
 
 def algorithmic_bytes(st, kernel: str) -> float:
@@ -378,12 +381,12 @@ def run_mine(args, workloads):
     for j in jobs:
         ctx = j["ctx"]
         ctx.set_timing(True)
-        names = KERNELS_2D if j["dim"] == 2 else KERNELS_3D
         for _ in range(frames_k):
             flush.zero_()
             torch.cuda.synchronize()
             (ctx.render2D if j["dim"] == 2 else ctx.render3D)(j["tape"])
             st = ctx.stats()
+            names = kernel_names(j["dim"], st.n_launches)
             for name, ms in zip(names, list(st.kernel_ms)[: st.n_launches]):
                 per_kernel[name] = per_kernel.get(name, 0.0) + ms / frames_k
             for name in set(names):

@@ -269,7 +269,7 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
     ts.init(s_dyn + warp * Stream::stride(), a.arena, a.arena_cap);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
     Slots2<REMAP> slots;
-    slots.base = smem_addr(s_dyn + kEvalWarps * Stream::stride()) + (warp * n_rows * 32 + lane) * 8;
+    slots.base = smem_addr(s_dyn + kEvalWarps * Stream::stride()) + (warp * n_rows * 32 + lane) * 8 - (REMAP ? 0 : 256);
     slots.limit = uint32_t(n_rows) * 256u;
 
     uint64_t* const arena = a.arena;
@@ -367,9 +367,11 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                 Y = iv_div(r[1], r[2]);
                 Z = iv(a.z, a.z);
             }
-            slots.st(off_out2(h), X);
-            slots.st(off_lhs2(h), Y);
-            slots.st(off_rhs2(h), Z);
+            // an axis the tape never reads has slot id 0 (context.cu:210-213 writes slot 0 there,
+            // harmlessly; here id 0 has no row at all)
+            if (REMAP || off_out2(h)) slots.st(off_out2(h), X);
+            if (REMAP || off_lhs2(h)) slots.st(off_lhs2(h), Y);
+            if (REMAP || off_rhs2(h)) slots.st(off_rhs2(h), Z);
         }
 
         // ---- forward walk (context.cu:223-287) -------------------------------------
@@ -1105,12 +1107,11 @@ k_upsample_filled(const int32_t* __restrict__ prev, int32_t* __restrict__ image,
 // Runs clauses starting at the cell AFTER `cp` until it meets one it does not handle - END, JUMP,
 // or a trigonometric libdevice function (EXP and LOG are handlers: libdevice's own PTX) - and returns with cp on that cell and its two words
 // in w / imm.  `sb` is this lane's slot base in shared space (slot s at sb + 256 s).
-// G = tiles per warp (1, 2 or 4): the same loop over G f32 pairs per slot and lane.
-// U = clauses per trip (1 or 2): see tools/gen_float_loop.py.
-template <int G, int U>
+// G = tiles per warp (1, 2 or 4): the same loop over G f32 pairs per slot and lane (tools/gen_float_loop.py).
+template <int G>
 __device__ __forceinline__ void run_float_clauses(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb);
 template <>
-__device__ __forceinline__ void run_float_clauses<1, 1>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
+__device__ __forceinline__ void run_float_clauses<1>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
 {
     asm volatile(
 #include "float_loop_ptx.inc"
@@ -1119,7 +1120,7 @@ __device__ __forceinline__ void run_float_clauses<1, 1>(uint32_t& cp, uint32_t& 
         : "memory");
 }
 template <>
-__device__ __forceinline__ void run_float_clauses<2, 1>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
+__device__ __forceinline__ void run_float_clauses<2>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
 {
     asm volatile(
 #include "float_loop_ptx_g2.inc"
@@ -1128,37 +1129,10 @@ __device__ __forceinline__ void run_float_clauses<2, 1>(uint32_t& cp, uint32_t& 
         : "memory");
 }
 template <>
-__device__ __forceinline__ void run_float_clauses<4, 1>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
+__device__ __forceinline__ void run_float_clauses<4>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
 {
     asm volatile(
 #include "float_loop_ptx_g4.inc"
-        : "+r"(cp), "=&r"(w), "=&r"(imm)
-        : "r"(sb)
-        : "memory");
-}
-template <>
-__device__ __forceinline__ void run_float_clauses<1, 2>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
-{
-    asm volatile(
-#include "float_loop_ptx_u2.inc"
-        : "+r"(cp), "=&r"(w), "=&r"(imm)
-        : "r"(sb)
-        : "memory");
-}
-template <>
-__device__ __forceinline__ void run_float_clauses<2, 2>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
-{
-    asm volatile(
-#include "float_loop_ptx_g2u2.inc"
-        : "+r"(cp), "=&r"(w), "=&r"(imm)
-        : "r"(sb)
-        : "memory");
-}
-template <>
-__device__ __forceinline__ void run_float_clauses<4, 2>(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb)
-{
-    asm volatile(
-#include "float_loop_ptx_g4u2.inc"
         : "+r"(cp), "=&r"(w), "=&r"(imm)
         : "r"(sb)
         : "memory");
@@ -1216,7 +1190,7 @@ __device__ __forceinline__ float2 float_clause_libdevice(uint32_t op, float2 L)
 // Walks one tape for the G tiles of a work item (two samples per tile and lane); r[g] receives
 // tile g's result pair.  Slot rows are 32 lanes x 8 G bytes: `sb` is this lane's address in row 0
 // and tile g sits 8 g bytes further.
-template <bool REMAP, int G, int U>
+template <bool REMAP, int G>
 __device__ __forceinline__ void walk_float(TapeStream<REMAP, REMAP>& ts, int tape, Slots2<REMAP>& slots, unsigned& cells,
                                            float2 (&r)[G])
 {
@@ -1233,7 +1207,7 @@ __device__ __forceinline__ void walk_float(TapeStream<REMAP, REMAP>& ts, int tap
             w = d.x;
             immb = d.y;
         } else {
-            run_float_clauses<G, U>(cp, w, immb, slots.base);
+            run_float_clauses<G>(cp, w, immb, slots.base);
         }
         const uint32_t op = w & 0xff;
         if (op <= OP_JUMP) {
@@ -1273,7 +1247,7 @@ __device__ __forceinline__ void unpack_item(int32_t code, int& start, int& count
 }
 
 // 2D: one warp per work item of up to G surviving 8x8 tiles, two pixels per tile and lane (y and y + 4).
-template <bool REMAP, bool HEAT = false, int G = 1, int U = 1>
+template <bool REMAP, bool HEAT = false, int G = 1>
 __global__ void __launch_bounds__(kFloatMaxThreads)
 k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 {
@@ -1285,7 +1259,8 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
     ts.init(s_dyn + warp * Stream::stride(), a.arena, a.arena_cap);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
     Slots2<REMAP> slots;
-    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * G) * 8;
+    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * G) * 8 -
+                 (REMAP ? 0 : 256 * G);       // slot id s lives in row s - 1 (id 0 is "no operand")
     slots.limit = uint32_t(n_rows) * 256u;
     const uint64_t* const arena = a.arena;
     unsigned long long st_tiles = 0, st_cells = 0, st_items = 0;
@@ -1323,14 +1298,14 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
                 slots.st(off_lhs2(h), Y);
                 slots.st(off_rhs2(h), make_float2(a.z, a.z));
             } else {
-                sts_f2(slots.base + off_out2(h) + 8 * g, X);
-                sts_f2(slots.base + off_lhs2(h) + 8 * g, Y);
-                sts_f2(slots.base + off_rhs2(h) + 8 * g, make_float2(a.z, a.z));
+                if (off_out2(h)) sts_f2(slots.base + off_out2(h) + 8 * g, X);          // id 0: axis unused, no row
+                if (off_lhs2(h)) sts_f2(slots.base + off_lhs2(h) + 8 * g, Y);
+                if (off_rhs2(h)) sts_f2(slots.base + off_rhs2(h) + 8 * g, make_float2(a.z, a.z));
             }
         }
         unsigned cells = 0;
         float2 r[G];
-        walk_float<REMAP, G, U>(ts, tape, slots, cells, r);
+        walk_float<REMAP, G>(ts, tape, slots, cells, r);
         #pragma unroll
         for (int g = 0; g < G; ++g) {
             if (g >= count) break;
@@ -1358,7 +1333,7 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 // Root tiles are issued highest-z first and children inherit that order, so the
 // list is roughly front-to-back and the per-lane early-out below (the
 // reference's, context.cu:852-864) culls most of what lies behind the surface.
-template <bool REMAP, bool HEAT = false, int G = 1, int U = 1>
+template <bool REMAP, bool HEAT = false, int G = 1>
 __global__ void __launch_bounds__(kFloatMaxThreads)
 k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
 {
@@ -1370,7 +1345,8 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
     ts.init(s_dyn + warp * Stream::stride(), a.arena, a.arena_cap);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
     Slots2<REMAP> slots;
-    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * G) * 8;
+    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * G) * 8 -
+                 (REMAP ? 0 : 256 * G);       // slot id s lives in row s - 1 (id 0 is "no operand")
     slots.limit = uint32_t(n_rows) * 256u;
     const uint64_t* const arena = a.arena;
     unsigned long long st_tiles = 0, st_cells = 0, st_items = 0;
@@ -1423,14 +1399,14 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
                 slots.st(off_lhs2(hdr), Y);
                 slots.st(off_rhs2(hdr), Z);
             } else {
-                sts_f2(slots.base + off_out2(hdr) + 8 * g, X);
-                sts_f2(slots.base + off_lhs2(hdr) + 8 * g, Y);
-                sts_f2(slots.base + off_rhs2(hdr) + 8 * g, Z);
+                if (off_out2(hdr)) sts_f2(slots.base + off_out2(hdr) + 8 * g, X);      // id 0: axis unused, no row
+                if (off_lhs2(hdr)) sts_f2(slots.base + off_lhs2(hdr) + 8 * g, Y);
+                if (off_rhs2(hdr)) sts_f2(slots.base + off_rhs2(hdr) + 8 * g, Z);
             }
         }
         unsigned cells = 0;
         float2 r[G];
-        walk_float<REMAP, G, U>(ts, tape, slots, cells, r);
+        walk_float<REMAP, G>(ts, tape, slots, cells, r);
         #pragma unroll
         for (int g = 0; g < G; ++g) {
             if (alive[g]) {
@@ -1662,7 +1638,9 @@ static size_t walk_smem(int n_rows, bool remap, int warps = kEvalWarps, int grou
 }
 // Shared-memory value rows per warp: one per slot id, or a fixed budget when slots are renamed.
 int walk_rows(int n_slots) {
-    if (!use_remap(n_slots)) return n_slots;
+    // Slot id 0 means "no operand" (src/tape.cpp:70) and never holds a value: ids 1 .. n_slots - 1
+    // get the rows, and the walkers address row (id - 1) by starting one row early.
+    if (!use_remap(n_slots)) return n_slots > 1 ? n_slots - 1 : 1;
     static const char* env = getenv("MPRB_REMAP_ROWS");
     const int rows = env ? atoi(env) : kRemapRowsDefault;
     return rows < kRemapRowsMin ? kRemapRowsMin : (rows > 128 ? 128 : rows);
@@ -1717,18 +1695,11 @@ bool use_local_normals(int n_slots) {
     return n_slots > 18;
 }
 
-// Float-pass variants without renaming: G tiles per work item x U clauses per loop trip.
-int float_unroll() {
-    static const char* env = getenv("MPRB_FLOAT_UNROLL");
-    return env ? (atoi(env) >= 2 ? 2 : 1) : 1;
-}
-template <typename F> static auto pick_float(int G, int U, F f) {
-    if (G == 4) return U == 2 ? f(std::integral_constant<int, 4>(), std::integral_constant<int, 2>())
-                              : f(std::integral_constant<int, 4>(), std::integral_constant<int, 1>());
-    if (G == 2) return U == 2 ? f(std::integral_constant<int, 2>(), std::integral_constant<int, 2>())
-                              : f(std::integral_constant<int, 2>(), std::integral_constant<int, 1>());
-    return U == 2 ? f(std::integral_constant<int, 1>(), std::integral_constant<int, 2>())
-                  : f(std::integral_constant<int, 1>(), std::integral_constant<int, 1>());
+// Float-pass variants without renaming: G tiles per work item.
+template <typename F> static auto pick_float(int G, F f) {
+    if (G == 4) return f(std::integral_constant<int, 4>());
+    if (G == 2) return f(std::integral_constant<int, 2>());
+    return f(std::integral_constant<int, 1>());
 }
 
 // Also pin the L1/shared split to "all shared" for the shared-memory variants: occupancy there
@@ -1765,12 +1736,11 @@ void init_kernels(int max_smem_optin) {
     opt_in(k_eval_pixels<true, true>, max_smem_optin);
     opt_in(k_eval_voxels<true, true>, max_smem_optin);
     for (int G = 1; G <= 4; G *= 2)
-        for (int U = 1; U <= 2; ++U)
-            pick_float(G, U, [&](auto g, auto u) {
-                opt_in(k_eval_pixels<false, false, decltype(g)::value, decltype(u)::value>, max_smem_optin);
-                opt_in(k_eval_voxels<false, false, decltype(g)::value, decltype(u)::value>, max_smem_optin);
-                return 0;
-            });
+        pick_float(G, [&](auto g) {
+            opt_in(k_eval_pixels<false, false, decltype(g)::value>, max_smem_optin);
+            opt_in(k_eval_voxels<false, false, decltype(g)::value>, max_smem_optin);
+            return 0;
+        });
     opt_in(k_normals<false>, max_smem_optin);
     opt_in(k_eval_pixels<true>, max_smem_optin);
     opt_in(k_eval_voxels<true>, max_smem_optin);
@@ -1826,8 +1796,8 @@ void launch_eval_pixels(const EvalVoxelsArgs& a, const Mat3& mat, int grid, cuda
         if (local) k_eval_pixels<true, true><<<grid, fw * 32, smem, s>>>(a, mat);
         else k_eval_pixels<false, true><<<grid, fw * 32, smem, s>>>(a, mat);
     } else if (local) k_eval_pixels<true><<<grid, fw * 32, smem, s>>>(a, mat);
-    else pick_float(G, float_unroll(), [&](auto g, auto u) {
-        k_eval_pixels<false, false, decltype(g)::value, decltype(u)::value><<<grid, fw * 32, smem, s>>>(a, mat);
+    else pick_float(G, [&](auto g) {
+        k_eval_pixels<false, false, decltype(g)::value><<<grid, fw * 32, smem, s>>>(a, mat);
         return 0;
     });
 }
@@ -1841,8 +1811,8 @@ void launch_eval_voxels(const EvalVoxelsArgs& a, const Mat4& mat, int grid, cuda
         if (local) k_eval_voxels<true, true><<<grid, fw * 32, smem, s>>>(a, mat);
         else k_eval_voxels<false, true><<<grid, fw * 32, smem, s>>>(a, mat);
     } else if (local) k_eval_voxels<true><<<grid, fw * 32, smem, s>>>(a, mat);
-    else pick_float(G, float_unroll(), [&](auto g, auto u) {
-        k_eval_voxels<false, false, decltype(g)::value, decltype(u)::value><<<grid, fw * 32, smem, s>>>(a, mat);
+    else pick_float(G, [&](auto g) {
+        k_eval_voxels<false, false, decltype(g)::value><<<grid, fw * 32, smem, s>>>(a, mat);
         return 0;
     });
 }
@@ -1892,13 +1862,13 @@ int occupancy_eval_voxels(int dim, int n_slots, int group) {
     const size_t smem = walk_smem(walk_rows(n_slots), local, fw, group, true);
     if (dim == 3) {
         if (local) return occ(k_eval_voxels<true>, smem, fw * 32);
-        return pick_float(group, float_unroll(), [&](auto g, auto u) {
-            return occ(k_eval_voxels<false, false, decltype(g)::value, decltype(u)::value>, smem, fw * 32);
+        return pick_float(group, [&](auto g) {
+            return occ(k_eval_voxels<false, false, decltype(g)::value>, smem, fw * 32);
         });
     }
     if (local) return occ(k_eval_pixels<true>, smem, fw * 32);
-    return pick_float(group, float_unroll(), [&](auto g, auto u) {
-        return occ(k_eval_pixels<false, false, decltype(g)::value, decltype(u)::value>, smem, fw * 32);
+    return pick_float(group, [&](auto g) {
+        return occ(k_eval_pixels<false, false, decltype(g)::value>, smem, fw * 32);
     });
 }
 

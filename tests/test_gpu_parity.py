@@ -10,7 +10,7 @@ import pytest
 
 import oracle
 import parity
-from conftest import golden_cases, load_tape
+from conftest import ROOT, golden_cases, load_tape
 from mpr_b200 import capi, sharding
 
 pytestmark = pytest.mark.gpu
@@ -268,6 +268,30 @@ def test_effects_match_cpu_restatement(model, size):
         assert (diff != 0).mean() <= 1e-3, (model, shaded, float((diff != 0).mean()))
     fx.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("group", [2, 4])
+@pytest.mark.parametrize("name", ["bear_3d_256", "hello_world_3d_128", "hello_world_2d_256"])
+def test_float_pass_work_items_of_several_tiles_give_the_reference_frame(name, group):
+    """The float pass can walk one tape for 2 or 4 tiles at a time (tiles of a work item share their
+    tape; MPRB_FLOAT_GROUP, read once per process): same frame as the reference build, fewer items than
+    tiles, and the arena holds shared tapes once."""
+    import json
+    import os
+    import subprocess
+    import sys
+    model, dim, size = name.rsplit("_", 2)
+    want = json.loads((ROOT / "tests" / "golden" / "ref" / f"{name}.json").read_text())
+    env = dict(os.environ, MPRB_FLOAT_GROUP=str(group))
+    r = subprocess.run([sys.executable, str(ROOT / "tools" / "frame_digest.py"), model, dim[0], size],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    assert got["image"] == want["image"]["sha"]
+    if dim[0] == "3":
+        assert got["normals"] == want["normals"]["sha"]
+    assert 0 < got["f_items"] < got["f_tiles"]
+    assert 0 < got["p_written"] < got["p_kept"]
 
 
 @pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built")

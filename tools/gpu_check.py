@@ -49,6 +49,9 @@ CASES = [
     ("involute_gear_2d", 2, 3072),
     ("bear", 3, 1536),
     ("prospero", 2, 2048),
+    ("prospero", 2, 512),
+    ("prospero", 2, 3072),
+    ("bear", 3, 512),
 ]
 
 SUBTAPES = 6400000   # the reference arm is built with -DBIG_SERVER
