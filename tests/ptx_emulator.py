@@ -304,6 +304,10 @@ class LoopMachine(Machine):
                 addr = self.val(m.group(1))
                 self.smem[addr] = self.val(m.group(2))
                 self.smem[addr + 4] = self.val(m.group(3))
+            elif op == "ld.shared.b32":
+                am = re.search(r"\[(\w+|%\d+)(?:\+(\d+))?\]", ins)
+                addr = self.val(am.group(1)) + int(am.group(2) or 0)
+                self.set(ins.split(None, 1)[1].split(",")[0], self.smem.get(addr, 0))
             elif op in ("ld.shared.b64", "ld.shared.v2.b64", "st.shared.b64", "st.shared.v2.b64"):
                 # 64-bit registers hold two f32 patterns (lo | hi << 32): the float loop's sample pairs
                 am = re.search(r"\[(\w+|%\d+)(?:\+(\d+))?\]", ins)
