@@ -322,7 +322,7 @@ int cached_occupancy(mprb_ctx* c, int kind, int dim, bool root, int n_slots, int
     if (itr != c->occ_cache.end()) return itr->second;
     int n = 0;
     if (kind == 0) n = occupancy_eval_tiles(dim, root, n_slots);
-    else if (kind == 1) n = occupancy_eval_voxels(dim, n_slots, group);
+    else if (kind == 1) n = float_ctas(dim, n_slots, group, float_tmem(n_slots, false) && group == 2);
     else n = occupancy_normals(n_slots);
     n = std::max(n, 1);
     c->occ_cache[key] = n;
@@ -535,6 +535,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         va.items = c->float_items;
         va.n_items = &c->ctl->n_active[3];
         va.group = brute ? 1 : group;
+        va.tmem = (!brute && float_tmem(n_slots, heat)) ? 1 : 0;
         va.tps = uint32_t(S / px_of[n_levels - 1]);
         va.ctl = c->ctl;
         va.queue = &c->ctl->queue[q++];

@@ -31,6 +31,7 @@
 // reference src/context.cu; line numbers are cited at each step.  How it is
 // scheduled (work units, memory layout, fusion, queues) is specific to this
 // implementation.
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <type_traits>
@@ -406,8 +407,9 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
                 continue;
             }
             const float imm = __uint_as_float(d.y);
-            const ival L = slots.ld(off_lhs2(w));
-            const ival R = slots.ld(off_rhs2(w));
+            // without renaming slot id 0 ("no operand") has no row: nothing is loaded for it
+            const ival L = (REMAP || off_lhs2(w)) ? slots.ld(off_lhs2(w)) : iv(0.0f, 0.0f);
+            const ival R = (REMAP || off_rhs2(w)) ? slots.ld(off_rhs2(w)) : iv(0.0f, 0.0f);
             ival o;
             if (!REMAP) {
                 // the opcodes the PTX loop hands back
@@ -1138,6 +1140,29 @@ __device__ __forceinline__ void run_float_clauses<4>(uint32_t& cp, uint32_t& w, 
         : "memory");
 }
 
+// G = 2 with tile 1's value rows in TENSOR MEMORY (tools/gen_float_loop.py, `tmem`): tb = address of this
+// warp's column group minus 2 (slot id s -> columns 2 (s - 1), 2 (s - 1) + 1).
+__device__ __forceinline__ void run_float_clauses_tm(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb, uint32_t tb)
+{
+    asm volatile(
+#include "float_loop_ptx_g2t.inc"
+        : "+r"(cp), "=&r"(w), "=&r"(imm)
+        : "r"(sb), "r"(tb)
+        : "memory");
+}
+__device__ __forceinline__ void tm_st2(uint32_t taddr, float2 v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ float2 tm_ld2(uint32_t taddr) {      // waits for earlier stores and for the load itself
+    float2 v;
+    asm volatile("tcgen05.wait::st.sync.aligned;\n"
+                 "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=f"(v.x), "=f"(v.y) : "r"(taddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t tm_col(uint32_t off256) { return off256 >> 7; }   // slot * 256 -> slot * 2
+
 // One clause in C++ (context.cu:887-920): the slot-renaming variant runs every clause through
 // this, the PTX loop above only the transcendental ones.
 __device__ __forceinline__ float2 float_clause(uint32_t op, float2 L, float2 R, float imm)
@@ -1190,12 +1215,13 @@ __device__ __forceinline__ float2 float_clause_libdevice(uint32_t op, float2 L)
 // Walks one tape for the G tiles of a work item (two samples per tile and lane); r[g] receives
 // tile g's result pair.  Slot rows are 32 lanes x 8 G bytes: `sb` is this lane's address in row 0
 // and tile g sits 8 g bytes further.
-template <bool REMAP, int G>
+template <bool REMAP, int G, bool TM>
 __device__ __forceinline__ void walk_float(TapeStream<REMAP, REMAP>& ts, int tape, Slots2<REMAP>& slots, unsigned& cells,
-                                           float2 (&r)[G])
+                                           float2 (&r)[G], uint32_t tb)
 {
-    constexpr int SHIFT = G == 4 ? 2 : (G == 2 ? 1 : 0);
+    constexpr int SHIFT = TM ? 0 : (G == 4 ? 2 : (G == 2 ? 1 : 0));      // TM: shared-memory rows keep the G = 1 layout
     static_assert(!REMAP || G == 1, "renamed slots: one tile per warp");
+    static_assert(!TM || G == 2, "tensor-memory rows: two tiles per warp");
     if (ts.fetch(tape) && !REMAP) annotate_chunk<kFastOps, kUsesLhs, kUsesRhs, SHIFT>(ts.buf);
     uint32_t cp = ts.rd + ((tape & (kChunk - 1)) << 3);
     uint32_t seg = cp;
@@ -1206,6 +1232,8 @@ __device__ __forceinline__ void walk_float(TapeStream<REMAP, REMAP>& ts, int tap
             const uint2 d = lds_u2(cp);
             w = d.x;
             immb = d.y;
+        } else if (TM) {
+            run_float_clauses_tm(cp, w, immb, slots.base, tb);
         } else {
             run_float_clauses<G>(cp, w, immb, slots.base);
         }
@@ -1222,6 +1250,9 @@ __device__ __forceinline__ void walk_float(TapeStream<REMAP, REMAP>& ts, int tap
         if (REMAP) {
             const float2 L = slots.ld(off_lhs2(w));
             slots.st(off_out2(w), float_clause(op, L, slots.ld(off_rhs2(w)), __uint_as_float(immb)));
+        } else if (TM) {
+            sts_f2(slots.base + off_out2(w), float_clause_libdevice(op, lds_f2(slots.base + off_lhs2(w))));
+            tm_st2(tb + tm_col(off_out2(w)), float_clause_libdevice(op, tm_ld2(tb + tm_col(off_lhs2(w)))));
         } else {
             #pragma unroll
             for (int g = 0; g < G; ++g) {
@@ -1232,6 +1263,9 @@ __device__ __forceinline__ void walk_float(TapeStream<REMAP, REMAP>& ts, int tap
     }
     if (REMAP) {
         r[0] = slots.ld(off_out2(w));
+    } else if (TM) {
+        r[0] = lds_f2(slots.base + off_out2(w));
+        r[1 % G] = tm_ld2(tb + tm_col(off_out2(w)));
     } else {
         #pragma unroll
         for (int g = 0; g < G; ++g) r[g] = lds_f2(slots.base + off_out2(w) + 8 * g);
@@ -1247,7 +1281,7 @@ __device__ __forceinline__ void unpack_item(int32_t code, int& start, int& count
 }
 
 // 2D: one warp per work item of up to G surviving 8x8 tiles, two pixels per tile and lane (y and y + 4).
-template <bool REMAP, bool HEAT = false, int G = 1>
+template <bool REMAP, bool HEAT = false, int G = 1, bool TM = false>
 __global__ void __launch_bounds__(kFloatMaxThreads)
 k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
 {
@@ -1258,10 +1292,28 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
     Stream ts;
     ts.init(s_dyn + warp * Stream::stride(), a.arena, a.arena_cap);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
+    constexpr int GS = TM ? 1 : G;     // tiles whose rows live in shared memory
     Slots2<REMAP> slots;
-    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * G) * 8 -
-                 (REMAP ? 0 : 256 * G);       // slot id s lives in row s - 1 (id 0 is "no operand")
+    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * GS) * 8 -
+                 (REMAP ? 0 : 256 * GS);      // slot id s lives in row s - 1 (id 0 is "no operand")
     slots.limit = uint32_t(n_rows) * 256u;
+    // TM: tile 1's value rows live in tensor memory.  Warp w owns TMEM lanes 32 (w % 4) .. + 31 (the
+    // hardware's rule) and the column group w / 4 of the CTA's allocation, 2 n_rows columns wide.
+    uint32_t tb = 0;
+    // the allocation's address lands in the padding behind warp 0's chunk buffer and mbarrier (no static
+    // shared memory: the kernels opt in to the whole dynamic carve-out)
+    uint32_t& s_tmem = *reinterpret_cast<uint32_t*>(s_dyn + kChunk * 8 + 16);
+    if (TM) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"l"((unsigned long long)__cvta_generic_to_shared(&s_tmem)), "r"(a.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tb = s_tmem + ((uint32_t(warp & 3) * 32u) << 16) + uint32_t(warp >> 2) * uint32_t(2 * n_rows) - 2u;
+    }
     const uint64_t* const arena = a.arena;
     unsigned long long st_tiles = 0, st_cells = 0, st_items = 0;
     const uint32_t root_hdr = uint32_t(arena[0]);
@@ -1270,7 +1322,7 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
     const int size = tps * 8;
     const float recip = 1.0f / float(tps * 8u);
     const float* m = mat.d;
-    constexpr int SHIFT = G == 4 ? 2 : (G == 2 ? 1 : 0);
+    constexpr int SHIFT = TM ? 0 : (G == 4 ? 2 : (G == 2 ? 1 : 0));
 
     for (;;) {
         const int item = warp_next(a.queue);
@@ -1298,14 +1350,20 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
                 slots.st(off_lhs2(h), Y);
                 slots.st(off_rhs2(h), make_float2(a.z, a.z));
             } else {
-                if (off_out2(h)) sts_f2(slots.base + off_out2(h) + 8 * g, X);          // id 0: axis unused, no row
-                if (off_lhs2(h)) sts_f2(slots.base + off_lhs2(h) + 8 * g, Y);
-                if (off_rhs2(h)) sts_f2(slots.base + off_rhs2(h) + 8 * g, make_float2(a.z, a.z));
+                if (TM && g == 1) {                                                     // tile 1: tensor memory
+                    if (off_out2(h)) tm_st2(tb + tm_col(off_out2(h)), X);
+                    if (off_lhs2(h)) tm_st2(tb + tm_col(off_lhs2(h)), Y);
+                    if (off_rhs2(h)) tm_st2(tb + tm_col(off_rhs2(h)), make_float2(a.z, a.z));
+                } else {
+                    if (off_out2(h)) sts_f2(slots.base + off_out2(h) + 8 * g, X);      // id 0: axis unused, no row
+                    if (off_lhs2(h)) sts_f2(slots.base + off_lhs2(h) + 8 * g, Y);
+                    if (off_rhs2(h)) sts_f2(slots.base + off_rhs2(h) + 8 * g, make_float2(a.z, a.z));
+                }
             }
         }
         unsigned cells = 0;
         float2 r[G];
-        walk_float<REMAP, G>(ts, tape, slots, cells, r);
+        walk_float<REMAP, G, TM>(ts, tape, slots, cells, r, tb);
         #pragma unroll
         for (int g = 0; g < G; ++g) {
             if (g >= count) break;
@@ -1327,13 +1385,20 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
         atomicAdd(&a.ctl->stats[ST_F_CELLS], st_cells);
         atomicAdd(&a.ctl->stats[ST_F_ITEMS], st_items);
     }
+    if (TM) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(a.tmem_cols) : "memory");
+    }
 }
 
 // 3D: one warp per work item of up to G surviving 4x4x4 tiles, two voxels per tile and lane (z and z + 2).
 // Root tiles are issued highest-z first and children inherit that order, so the
 // list is roughly front-to-back and the per-lane early-out below (the
 // reference's, context.cu:852-864) culls most of what lies behind the surface.
-template <bool REMAP, bool HEAT = false, int G = 1>
+template <bool REMAP, bool HEAT = false, int G = 1, bool TM = false>
 __global__ void __launch_bounds__(kFloatMaxThreads)
 k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
 {
@@ -1344,10 +1409,28 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
     Stream ts;
     ts.init(s_dyn + warp * Stream::stride(), a.arena, a.arena_cap);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
+    constexpr int GS = TM ? 1 : G;     // tiles whose rows live in shared memory
     Slots2<REMAP> slots;
-    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * G) * 8 -
-                 (REMAP ? 0 : 256 * G);       // slot id s lives in row s - 1 (id 0 is "no operand")
+    slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * GS) * 8 -
+                 (REMAP ? 0 : 256 * GS);      // slot id s lives in row s - 1 (id 0 is "no operand")
     slots.limit = uint32_t(n_rows) * 256u;
+    // TM: tile 1's value rows live in tensor memory.  Warp w owns TMEM lanes 32 (w % 4) .. + 31 (the
+    // hardware's rule) and the column group w / 4 of the CTA's allocation, 2 n_rows columns wide.
+    uint32_t tb = 0;
+    // the allocation's address lands in the padding behind warp 0's chunk buffer and mbarrier (no static
+    // shared memory: the kernels opt in to the whole dynamic carve-out)
+    uint32_t& s_tmem = *reinterpret_cast<uint32_t*>(s_dyn + kChunk * 8 + 16);
+    if (TM) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"l"((unsigned long long)__cvta_generic_to_shared(&s_tmem)), "r"(a.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tb = s_tmem + ((uint32_t(warp & 3) * 32u) << 16) + uint32_t(warp >> 2) * uint32_t(2 * n_rows) - 2u;
+    }
     const uint64_t* const arena = a.arena;
     unsigned long long st_tiles = 0, st_cells = 0, st_items = 0;
     const uint32_t root_hdr = uint32_t(arena[0]);
@@ -1356,7 +1439,7 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
     const int size = tps * 4;
     const float recip = 1.0f / float(tps * 4u);
     const float* m = mat.d;
-    constexpr int SHIFT = G == 4 ? 2 : (G == 2 ? 1 : 0);
+    constexpr int SHIFT = TM ? 0 : (G == 4 ? 2 : (G == 2 ? 1 : 0));
 
     for (;;) {
         const int item = warp_next(a.queue);
@@ -1399,14 +1482,20 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
                 slots.st(off_lhs2(hdr), Y);
                 slots.st(off_rhs2(hdr), Z);
             } else {
-                if (off_out2(hdr)) sts_f2(slots.base + off_out2(hdr) + 8 * g, X);      // id 0: axis unused, no row
-                if (off_lhs2(hdr)) sts_f2(slots.base + off_lhs2(hdr) + 8 * g, Y);
-                if (off_rhs2(hdr)) sts_f2(slots.base + off_rhs2(hdr) + 8 * g, Z);
+                if (TM && g == 1) {                                                     // tile 1: tensor memory
+                    if (off_out2(hdr)) tm_st2(tb + tm_col(off_out2(hdr)), X);
+                    if (off_lhs2(hdr)) tm_st2(tb + tm_col(off_lhs2(hdr)), Y);
+                    if (off_rhs2(hdr)) tm_st2(tb + tm_col(off_rhs2(hdr)), Z);
+                } else {
+                    if (off_out2(hdr)) sts_f2(slots.base + off_out2(hdr) + 8 * g, X);  // id 0: axis unused, no row
+                    if (off_lhs2(hdr)) sts_f2(slots.base + off_lhs2(hdr) + 8 * g, Y);
+                    if (off_rhs2(hdr)) sts_f2(slots.base + off_rhs2(hdr) + 8 * g, Z);
+                }
             }
         }
         unsigned cells = 0;
         float2 r[G];
-        walk_float<REMAP, G>(ts, tape, slots, cells, r);
+        walk_float<REMAP, G, TM>(ts, tape, slots, cells, r, tb);
         #pragma unroll
         for (int g = 0; g < G; ++g) {
             if (alive[g]) {
@@ -1428,6 +1517,13 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
         atomicAdd(&a.ctl->stats[ST_F_TILES], st_tiles);
         atomicAdd(&a.ctl->stats[ST_F_CELLS], st_cells);
         atomicAdd(&a.ctl->stats[ST_F_ITEMS], st_items);
+    }
+    if (TM) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(a.tmem_cols) : "memory");
     }
 }
 
@@ -1648,34 +1744,57 @@ int walk_rows(int n_slots) {
 // Tiles per work item of the float pass (1, 2 or 4).  Tiles of an item share their tape, and the
 // clause loop is bound by fetch + dispatch, so G tiles cost little more than one - but slot rows
 // grow G-fold and with them the shared memory per warp.  MPRB_FLOAT_GROUP overrides.
+// Default: two tiles per item with the second tile's rows in TENSOR MEMORY (float_tmem): the shared
+// memory footprint - and with it the number of resident warps - stays that of one tile.
+bool float_tmem(int n_slots, bool heat) {
+    if (use_remap(n_slots) || heat) return false;
+    static const char* env = getenv("MPRB_FLOAT_TMEM");
+    static const char* grp = getenv("MPRB_FLOAT_GROUP");
+    if (env) return env[0] != '0';
+    return grp == nullptr;              // an explicit group size means the shared-memory-only variants
+}
 int float_group(int n_slots, bool heat) {
     if (use_remap(n_slots) || heat) return 1;
+    if (float_tmem(n_slots, heat)) return 2;
     static const char* env = getenv("MPRB_FLOAT_GROUP");
     if (env) { const int v = atoi(env); return v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
     return 1;
 }
-// Warps per CTA of the float pass: the shape that keeps the most warps resident per SM given the
-// per-warp shared memory (value rows + chunk stream), 1 KB the driver reserves per CTA, and the
-// limits of 32 CTAs / 64 warps per SM.  MPRB_FLOAT_WARPS overrides.
-int float_warps(int n_slots, int group) {
+// CTA shape of the float pass: the warps per CTA (and CTAs per SM) that keep the most warps resident
+// given the per-warp shared memory (value rows + chunk stream), 1 KB the driver reserves per CTA, the
+// limits of 32 CTAs / 64 warps per SM and - with tensor-memory rows - the 512 TMEM columns of an SM:
+// a CTA allocates a power of two >= 32 columns, 2 n_rows for each group of 4 warps (the four warps of a
+// group sit in the four 32-lane quarters).  MPRB_FLOAT_WARPS overrides the warps per CTA.
+struct FloatShape { int warps, ctas, tmem_cols; };
+static int pow2_at_least(int v) { int p = 32; while (p < v) p *= 2; return p; }
+static FloatShape float_shape(int n_slots, int group, bool tmem) {
     static const char* env = getenv("MPRB_FLOAT_WARPS");
-    if (env) { const int v = atoi(env); return v < 1 ? 1 : (v > 32 ? 32 : v); }
     static int smem_per_sm = 0;
     if (!smem_per_sm) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     }
-    const size_t per_warp = walk_smem(walk_rows(n_slots), use_remap(n_slots), 1, group, true);
-    int best = 1, best_resident = 0;
+    const int rows = walk_rows(n_slots);
+    const size_t per_warp = walk_smem(rows, use_remap(n_slots), 1, tmem ? 1 : group, true);
+    FloatShape best = {1, 1, 32};
+    int best_resident = 0;
     for (int w = 1; w <= kFloatMaxThreads / 32; ++w) {
+        if (env && w != std::min(std::max(atoi(env), 1), 32)) continue;
         int ctas = int(size_t(smem_per_sm) / (w * per_warp + 1024));
         if (ctas > 32) ctas = 32;
         if (ctas > 64 / w) ctas = 64 / w;
-        if (ctas * w > best_resident) { best_resident = ctas * w; best = w; }
+        int cols = 32;
+        if (tmem) {
+            cols = pow2_at_least(((w + 3) / 4) * 2 * rows);
+            if (cols > 512) continue;
+            ctas = std::min(ctas, 512 / cols);
+        }
+        if (ctas * w > best_resident) { best_resident = ctas * w; best = {w, ctas, cols}; }
     }
     return best;
 }
+int float_warps(int n_slots, int group) { return float_shape(n_slots, group, false).warps; }
 // Renaming pays once per-id rows would leave fewer than ~24 warps per SM.
 bool use_remap(int n_slots) {
     static const char* force = getenv("MPRB_REMAP");
@@ -1695,11 +1814,14 @@ bool use_local_normals(int n_slots) {
     return n_slots > 18;
 }
 
-// Float-pass variants without renaming: G tiles per work item.
-template <typename F> static auto pick_float(int G, F f) {
-    if (G == 4) return f(std::integral_constant<int, 4>());
-    if (G == 2) return f(std::integral_constant<int, 2>());
-    return f(std::integral_constant<int, 1>());
+// Float-pass variants without renaming: G tiles per work item, tile 1 in tensor memory or not.
+template <typename F> static auto pick_float(int G, bool tmem, F f) {
+    typedef std::integral_constant<bool, true> T;
+    typedef std::integral_constant<bool, false> N;
+    if (tmem) return f(std::integral_constant<int, 2>(), T());
+    if (G == 4) return f(std::integral_constant<int, 4>(), N());
+    if (G == 2) return f(std::integral_constant<int, 2>(), N());
+    return f(std::integral_constant<int, 1>(), N());
 }
 
 // Also pin the L1/shared split to "all shared" for the shared-memory variants: occupancy there
@@ -1736,11 +1858,12 @@ void init_kernels(int max_smem_optin) {
     opt_in(k_eval_pixels<true, true>, max_smem_optin);
     opt_in(k_eval_voxels<true, true>, max_smem_optin);
     for (int G = 1; G <= 4; G *= 2)
-        pick_float(G, [&](auto g) {
-            opt_in(k_eval_pixels<false, false, decltype(g)::value>, max_smem_optin);
-            opt_in(k_eval_voxels<false, false, decltype(g)::value>, max_smem_optin);
-            return 0;
-        });
+        for (int T = 0; T <= (G == 2 ? 1 : 0); ++T)
+            pick_float(G, T != 0, [&](auto g, auto t) {
+                opt_in(k_eval_pixels<false, false, decltype(g)::value, decltype(t)::value>, max_smem_optin);
+                opt_in(k_eval_voxels<false, false, decltype(g)::value, decltype(t)::value>, max_smem_optin);
+                return 0;
+            });
     opt_in(k_normals<false>, max_smem_optin);
     opt_in(k_eval_pixels<true>, max_smem_optin);
     opt_in(k_eval_voxels<true>, max_smem_optin);
@@ -1787,32 +1910,53 @@ void launch_upsample_filled(int dim, const int32_t* prev, int32_t* image, int si
     else k_upsample_filled<2><<<grid, 256, 0, s>>>(prev, image, size);
 }
 
+// Launches the float pass with the CTA shape of float_shape(); with tensor-memory rows the dynamic shared
+// memory is padded so that no more CTAs fit an SM than its TMEM columns can serve (an allocation that
+// has to wait for columns would stall a whole CTA).
+static size_t float_pad_smem(const FloatShape& sh) {
+    int smem_per_sm = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    // one more CTA than `ctas` must not fit: ask for just over 1 / (ctas + 1) of the SM
+    return size_t(smem_per_sm) / size_t(sh.ctas + 1) - 1024 + 128;
+}
+
 void launch_eval_pixels(const EvalVoxelsArgs& a, const Mat3& mat, int grid, cudaStream_t s) {
     const bool local = use_remap(a.n_slots);
+    const bool tm = a.tmem != 0;
     const int G = a.group;
-    const int fw = float_warps(a.n_slots, G);
-    const size_t smem = walk_smem(a.n_rows, local, fw, G, true);
+    const FloatShape sh = float_shape(a.n_slots, G, tm);
+    EvalVoxelsArgs b = a;
+    b.tmem_cols = sh.tmem_cols;
+    size_t smem = walk_smem(a.n_rows, local, sh.warps, tm ? 1 : G, true);
+    if (tm) smem = std::max(smem, float_pad_smem(sh));
+    const int fw = sh.warps;
     if (a.heat) {
-        if (local) k_eval_pixels<true, true><<<grid, fw * 32, smem, s>>>(a, mat);
-        else k_eval_pixels<false, true><<<grid, fw * 32, smem, s>>>(a, mat);
-    } else if (local) k_eval_pixels<true><<<grid, fw * 32, smem, s>>>(a, mat);
-    else pick_float(G, [&](auto g) {
-        k_eval_pixels<false, false, decltype(g)::value><<<grid, fw * 32, smem, s>>>(a, mat);
+        if (local) k_eval_pixels<true, true><<<grid, fw * 32, smem, s>>>(b, mat);
+        else k_eval_pixels<false, true><<<grid, fw * 32, smem, s>>>(b, mat);
+    } else if (local) k_eval_pixels<true><<<grid, fw * 32, smem, s>>>(b, mat);
+    else pick_float(G, tm, [&](auto g, auto t) {
+        k_eval_pixels<false, false, decltype(g)::value, decltype(t)::value><<<grid, fw * 32, smem, s>>>(b, mat);
         return 0;
     });
 }
 
 void launch_eval_voxels(const EvalVoxelsArgs& a, const Mat4& mat, int grid, cudaStream_t s) {
     const bool local = use_remap(a.n_slots);
+    const bool tm = a.tmem != 0;
     const int G = a.group;
-    const int fw = float_warps(a.n_slots, G);
-    const size_t smem = walk_smem(a.n_rows, local, fw, G, true);
+    const FloatShape sh = float_shape(a.n_slots, G, tm);
+    EvalVoxelsArgs b = a;
+    b.tmem_cols = sh.tmem_cols;
+    size_t smem = walk_smem(a.n_rows, local, sh.warps, tm ? 1 : G, true);
+    if (tm) smem = std::max(smem, float_pad_smem(sh));
+    const int fw = sh.warps;
     if (a.heat) {
-        if (local) k_eval_voxels<true, true><<<grid, fw * 32, smem, s>>>(a, mat);
-        else k_eval_voxels<false, true><<<grid, fw * 32, smem, s>>>(a, mat);
-    } else if (local) k_eval_voxels<true><<<grid, fw * 32, smem, s>>>(a, mat);
-    else pick_float(G, [&](auto g) {
-        k_eval_voxels<false, false, decltype(g)::value><<<grid, fw * 32, smem, s>>>(a, mat);
+        if (local) k_eval_voxels<true, true><<<grid, fw * 32, smem, s>>>(b, mat);
+        else k_eval_voxels<false, true><<<grid, fw * 32, smem, s>>>(b, mat);
+    } else if (local) k_eval_voxels<true><<<grid, fw * 32, smem, s>>>(b, mat);
+    else pick_float(G, tm, [&](auto g, auto t) {
+        k_eval_voxels<false, false, decltype(g)::value, decltype(t)::value><<<grid, fw * 32, smem, s>>>(b, mat);
         return 0;
     });
 }
@@ -1856,20 +2000,10 @@ int occupancy_eval_tiles(int dim, bool root, int n_slots) {
     return local ? occ(k_eval_tiles<2, false, true>, smem) : occ(k_eval_tiles<2, false, false>, smem);
 }
 
-int occupancy_eval_voxels(int dim, int n_slots, int group) {
-    const bool local = use_remap(n_slots);
-    const int fw = float_warps(n_slots, group);
-    const size_t smem = walk_smem(walk_rows(n_slots), local, fw, group, true);
-    if (dim == 3) {
-        if (local) return occ(k_eval_voxels<true>, smem, fw * 32);
-        return pick_float(group, [&](auto g) {
-            return occ(k_eval_voxels<false, false, decltype(g)::value>, smem, fw * 32);
-        });
-    }
-    if (local) return occ(k_eval_pixels<true>, smem, fw * 32);
-    return pick_float(group, [&](auto g) {
-        return occ(k_eval_pixels<false, false, decltype(g)::value>, smem, fw * 32);
-    });
+// Resident CTAs per SM of the float pass (sizes its persistent grid).
+int float_ctas(int dim, int n_slots, int group, bool tmem) {
+    (void)dim;
+    return std::max(float_shape(n_slots, group, tmem).ctas, 1);
 }
 
 int occupancy_normals(int n_slots) {

@@ -108,6 +108,8 @@ struct EvalVoxelsArgs {
     const int32_t* items;     // work items: runs of up to `group` tiles sharing a tape (start * 8 + count)
     const int32_t* n_items;
     int32_t group;            // tiles per work item: 1, 2 or 4 (float_group)
+    int32_t tmem;             // 1: two tiles per item, tile 1's value rows in tensor memory (float_tmem)
+    int32_t tmem_cols;        // tensor-memory columns each CTA allocates (power of two, >= 32)
     uint32_t tps;             // survivor-level tiles per side (size/4 or size/8)
     FrameCtl* ctl;
     int32_t* queue;
@@ -150,9 +152,10 @@ void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_
 // Resident CTAs per SM for a given slot count (sizes the persistent grids).
 int walk_rows(int n_slots);
 int float_group(int n_slots, bool heat);
+bool float_tmem(int n_slots, bool heat);
+int float_ctas(int dim, int n_slots, int group, bool tmem);
 int float_warps(int n_slots, int group);
 int occupancy_eval_tiles(int dim, bool root, int n_slots);
-int occupancy_eval_voxels(int dim, int n_slots, int group);
 int occupancy_normals(int n_slots);
 
 }  // namespace mprb

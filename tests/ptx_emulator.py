@@ -260,6 +260,7 @@ class LoopMachine(Machine):
     def __init__(self, asm: str, regs, operands, smem):
         super().__init__(regs, operands)
         self.smem = smem
+        self.tmem = {}                  # tensor memory of this lane: column -> 32-bit word
         body = asm[asm.index("{") + 1: asm.rindex("}")]
         m = re.search(r"(\w+):\s*\.branchtargets([^;]*);", body)
         self.table = [t.strip() for t in m.group(2).replace("\n", " ").split(",")]
@@ -304,6 +305,21 @@ class LoopMachine(Machine):
                 addr = self.val(m.group(1))
                 self.smem[addr] = self.val(m.group(2))
                 self.smem[addr + 4] = self.val(m.group(3))
+            elif op.startswith("tcgen05.wait::"):
+                pass                                          # completion of asynchronous tensor-memory accesses
+            elif op.startswith("tcgen05.ld.") or op.startswith("tcgen05.st."):
+                # tensor memory as this lane sees it: 32-bit columns addressed by the column field
+                am = re.search(r"\[(\w+|%\d+)\]", ins)
+                col = self.val(am.group(1))
+                names = [x.strip() for x in re.search(r"\{(.*?)\}", ins).group(1).split(",")]
+                for k, name in enumerate(names):
+                    if op.startswith("tcgen05.ld."):
+                        self.set(name, self.tmem.get(col + k, 0))
+                    else:
+                        self.tmem[col + k] = self.val(name)
+            elif op == "bfe.u32":
+                a = [x.strip() for x in ins.split(None, 1)[1].split(",")]
+                self.set(a[0], (self.val(a[1]) >> self.val(a[2])) & ((1 << self.val(a[3])) - 1))
             elif op == "ld.shared.b32":
                 am = re.search(r"\[(\w+|%\d+)(?:\+(\d+))?\]", ins)
                 addr = self.val(am.group(1)) + int(am.group(2) or 0)

@@ -488,7 +488,8 @@ def test_generated_interval_loop_runs_whole_tapes_like_the_c_restatement():
         assert (m.r["cw"], m.r["n"], m.r["any"] != 0) == (cw, cnt, anyc != 0)
 
 
-@pytest.mark.parametrize("G,inc", [(1, "float_loop_ptx.inc"), (2, "float_loop_ptx_g2.inc"), (4, "float_loop_ptx_g4.inc")])
+@pytest.mark.parametrize("G,inc", [(1, "float_loop_ptx.inc"), (2, "float_loop_ptx_g2.inc"), (4, "float_loop_ptx_g4.inc"),
+                                   (2, "float_loop_ptx_g2t.inc")])
 def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation(G, inc):
     """Same for the float pass's loops (G tiles per warp, two samples per tile and lane; slot bytes
     pre-multiplied by G as annotate_chunk does), against numpy float32 arithmetic with the
@@ -502,8 +503,10 @@ def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation(G, 
     asm = load_asm(ROOT / "mpr_b200" / "csrc" / inc)
     ops = [o for o in sorted(mod.OPS) if o not in (10, 12)]
     rng = np.random.default_rng(5)
-    CH, SB = 0x1000, 0x4000
+    CH, SB, TB = 0x1000, 0x4000, 0x40
     f32 = np.float32
+    TM = inc.endswith("g2t.inc")      # tile 0 in shared-memory rows of 256 bytes, tile 1 in tensor-memory columns 2 s, 2 s + 1
+    GS = 1 if TM else G               # tiles per shared-memory row
 
     def clause(op, l, r, imm):
         with np.errstate(all="ignore"):
@@ -527,19 +530,25 @@ def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation(G, 
         smem = {}
         for j, c in enumerate(noted):
             w = c & 0xffffffff
-            w = (w & 0xff) | (((w >> 8) * G) << 8)          # slot ids -> row offsets in 256-byte units
+            w = (w & 0xff) | (((w >> 8) * GS) << 8)         # slot ids -> row offsets in 256-byte units
             smem[CH + 8 * j], smem[CH + 8 * j + 4] = w, c >> 32
         slots = {s: rng.normal(0, 2, 2 * G).astype(f32) for s in range(7)}
+        m = LoopMachine(asm, {"cp": CH - 8, "sb": SB, "tb": TB, "w": 0, "imm": 0},
+                        {"%0": "cp", "%1": "w", "%2": "imm", "%3": "sb", "%4": "tb"}, smem)
         for s, v in slots.items():
-            for k in range(2 * G):
-                smem[SB + 256 * G * s + 4 * k] = f2b(v[k])
-        m = LoopMachine(asm, {"cp": CH - 8, "sb": SB, "w": 0, "imm": 0},
-                        {"%0": "cp", "%1": "w", "%2": "imm", "%3": "sb"}, smem).execute()
+            for k in range(2 * GS):
+                smem[SB + 256 * GS * s + 4 * k] = f2b(v[k])
+            if TM:
+                m.tmem[TB + 2 * s], m.tmem[TB + 2 * s + 1] = f2b(v[2]), f2b(v[3])
+        m.execute()
         assert m.r["cp"] == CH + 8 * n and (m.r["w"] & 0xff) == 0
         for c in cells[:-1]:
             op, out, lhs, rhs = c & 0xff, (c >> 8) & 0xff, (c >> 16) & 0xff, (c >> 24) & 0xff
             imm = b2f(c >> 32)
             slots[out] = np.array([clause(op, slots[lhs][k], slots[rhs][k], imm) for k in range(2 * G)], dtype=f32)
         for s, v in slots.items():
-            got = np.array([b2f(smem[SB + 256 * G * s + 4 * k]) for k in range(2 * G)], dtype=f32)
+            got = [b2f(smem[SB + 256 * GS * s + 4 * k]) for k in range(2 * GS)]
+            if TM:
+                got += [b2f(m.tmem[TB + 2 * s]), b2f(m.tmem[TB + 2 * s + 1])]
+            got = np.array(got, dtype=f32)
             assert ((got == v) | (np.isnan(got) & np.isnan(v))).all(), (trial, s, got, v)
