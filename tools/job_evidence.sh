@@ -1,0 +1,18 @@
+set -x
+O=gpurun_out/r2ev; mkdir -p $O
+./build/ubench_dispatch > $O/ubench_dispatch.log 2>&1
+./build/ubench_tmem > $O/ubench_tmem.log 2>&1
+python bench.py --impl reference --steps 20 --warmup 5 > $O/bench_ref.json 2> $O/bench_ref.err
+python bench.py --steps 20 --warmup 5 > $O/bench_mine.json 2> $O/bench_mine.err
+python bench.py --impl reference --workload sweep --steps 10 --warmup 3 --no-cpu > $O/sweep_ref.json 2> $O/sweep_ref.err
+python bench.py --workload sweep --steps 10 --warmup 3 --no-cpu > $O/sweep_mine.json 2> $O/sweep_mine.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu > $O/bench_under_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_eval_voxels -s 2 -c 1 -o $O/prof_voxels python tools/run_one.py --model bear --dim 3 --size 1024 --frames 4 > $O/ncu_voxels.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_eval_tiles -s 5 -c 1 -o $O/prof_tiles_L2 python tools/run_one.py --model bear --dim 3 --size 1024 --frames 4 > $O/ncu_tiles.log 2>&1
+ncu --set full --clock-control none -k regex:k_normals -s 2 -c 1 -o $O/prof_normals python tools/run_one.py --model bear --dim 3 --size 1024 --frames 4 > $O/ncu_normals.log 2>&1
+ncu --set full --clock-control none -k regex:k_eval_root -s 2 -c 1 -o $O/prof_root python tools/run_one.py --model prospero --dim 2 --size 4096 --frames 4 > $O/ncu_root.log 2>&1
+timeout 900 compute-sanitizer --tool racecheck --print-limit 10 python tools/run_one.py --model bear --dim 3 --size 128 --frames 1 --subtapes 64000 > $O/racecheck_bear_ptxloop.log 2>&1
+timeout 900 compute-sanitizer --tool racecheck --print-limit 10 python tools/run_one.py --model prospero --dim 2 --size 256 --frames 1 --subtapes 64000 > $O/racecheck_prospero_remap.log 2>&1
+timeout 900 compute-sanitizer --tool memcheck --print-limit 10 python tools/run_one.py --model hello_world --dim 3 --size 128 --frames 2 --subtapes 64000 > $O/memcheck_hello_world.log 2>&1
+tail -3 $O/racecheck_bear_ptxloop.log $O/racecheck_prospero_remap.log $O/memcheck_hello_world.log
+ls -la $O
