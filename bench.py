@@ -195,6 +195,39 @@ def algorithmic_bytes(st, kernel: str) -> float:
     return 0.0
 
 
+OUT = sys.stdout          # where the JSON line goes (the real stdout, also after divert_stdout)
+_DIVERTED = None
+
+
+def divert_stdout(path):
+    """Everything written to file descriptor 1 from here on (Python, NCCL, torch) lands in `path`;
+    OUT keeps the real stdout."""
+    global OUT, _DIVERTED
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), "w")
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+    os.dup2(fd, 1)
+    os.close(fd)
+    _DIVERTED = [path, 0]
+
+
+def drain_diverted():
+    """Copies what has been diverted since the last call to stderr; returns those lines."""
+    if _DIVERTED is None:
+        return []
+    import ctypes
+    sys.stdout.flush()
+    ctypes.CDLL(None).fflush(None)            # NCCL writes through C stdio
+    with open(_DIVERTED[0], errors="replace") as f:
+        f.seek(_DIVERTED[1])
+        text = f.read()
+        _DIVERTED[1] = f.tell()
+    if text:
+        sys.stderr.write(text)
+        sys.stderr.flush()
+    return [l.strip() for l in text.splitlines()]
+
+
 def run_mine(args, workloads):
     import torch
     import torch.distributed as dist
@@ -207,12 +240,14 @@ def run_mine(args, workloads):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL reports its communicator (rank / nranks) at INFO level.  The log goes to a file per rank so
-        # that stdout stays the one JSON line; rank 0 copies the communicator lines to stderr and into the
-        # JSON line ("nccl") once the group is up.
+        # NCCL reports its communicator (rank / nranks) at INFO level, on stdout.  File descriptor 1 is
+        # pointed at a per-rank log for the whole run and the one JSON line goes to the real stdout
+        # (OUT) at the end; rank 0 copies the log to stderr and the communicator lines into the JSON line
+        # ("nccl") once the group is up.
         os.environ.setdefault("NCCL_DEBUG", os.environ.get("MPRB_NCCL_DEBUG", "INFO"))
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        nccl_log = os.environ.setdefault("NCCL_DEBUG_FILE", f"/tmp/mprb_nccl_{os.getpid()}_%h_%p.log")
+        os.environ.pop("NCCL_DEBUG_FILE", None)
+        divert_stdout(f"/tmp/mprb_stdout_{os.getpid()}_rank{rank}.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     class DevArray:   # wraps a raw device pointer for torch.as_tensor
@@ -247,18 +282,8 @@ def run_mine(args, workloads):
         dist.barrier()                        # first collective: the communicator exists after this
         torch.cuda.synchronize()
         if rank == 0:
-            import glob
-            import socket
-            lines = []
-            pat = nccl_log.replace("%h", socket.gethostname()).replace("%p", str(os.getpid()))
-            for f in glob.glob(pat) + glob.glob(nccl_log.replace("%h", "*").replace("%p", "*")):
-                try:
-                    lines += [l.strip() for l in open(f, errors="replace") if "nranks" in l or "NCCL version" in l]
-                except OSError:
-                    pass
+            lines = [l for l in drain_diverted() if "nranks" in l or "NCCL version" in l]
             lines = sorted(set(lines))[:8]
-            for l in lines:
-                print(l, file=sys.stderr, flush=True)
             nccl_info = {"world_size": dist.get_world_size(), "backend": dist.get_backend(), "log_lines": lines}
 
     def gather(job):
@@ -455,7 +480,8 @@ def run_mine(args, workloads):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(workloads)
-        print(json.dumps(line), flush=True)
+        drain_diverted()
+        print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     if rank == 0 and mismatched:

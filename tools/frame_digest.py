@@ -18,7 +18,8 @@ def main():
     (ctx.render2D if dim == 2 else ctx.render3D)(tape)
     st = ctx.stats()
     out = {"image": parity.digest(ctx.image()), "f_tiles": int(st.f_tiles), "f_items": int(st.f_items),
-           "p_kept": int(sum(st.p_kept)), "p_written": int(st.p_written)}
+           "p_kept": int(sum(st.p_kept)), "p_written": int(st.p_written), "i_tiles": [int(v) for v in st.i_tiles],
+           "i_sub_tiles": int(st.i_sub_tiles), "n_active": [int(v) for v in st.n_active]}
     if dim == 3:
         out["normals"] = parity.digest(ctx.normals())
     print(json.dumps(out))

@@ -49,7 +49,8 @@ def main():
         row = {"gpu_ms": float(np.mean(gpu)), "gpu_ms_min": float(np.min(gpu)),
                "kernels": {n: round(float(v), 4) for n, v in zip(names, k)},
                "float_tiles": int(st.f_tiles), "float_cells": int(st.f_cells), "float_items": int(st.f_items),
-               "push_tiles": list(st.p_tiles), "push_kept": list(st.p_kept), "push_written": int(st.p_written)}
+               "push_tiles": list(st.p_tiles), "push_kept": list(st.p_kept), "push_written": int(st.p_written),
+               "n_active": list(st.n_active), "interval_tiles": list(st.i_tiles), "interval_cells": list(st.i_cells)}
         out[case] = row
         print(case, json.dumps(row), flush=True)
         ctx.close()
