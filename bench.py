@@ -266,6 +266,26 @@ def run_mine(args, workloads):
         job = dict(model=model, dim=dim, size=size, ctx=ctx, tape=tape, cells=cells, keep=cells_pinned,
                    out_img=out_img, out_nrm=out_nrm)
         if world > 1:
+            # End-to-end frames land in ONE page-locked host frame shared by the ranks' processes (a shared-memory
+            # file every rank maps and registers with CUDA): each GPU stores the blocks it owns over its own
+            # PCIe link (mprb_ctx_publish) and nobody gathers the frame on a device first.
+            n_int = size * size * (2 if dim == 3 else 1)
+            path = [f"/dev/shm/mprb_bench_{os.getpid()}_{len(jobs)}" if rank == 0 else None]
+            dist.broadcast_object_list(path, src=0)
+            if rank == 0:
+                with open(path[0], "wb") as f:
+                    f.truncate(n_int * 4)
+            dist.barrier()
+            shared = torch.from_file(path[0], shared=True, size=n_int, dtype=torch.int32)
+            err = torch.cuda.cudart().cudaHostRegister(shared.data_ptr(), n_int * 4, 3)     # portable | mapped
+            if int(err) != 0:
+                raise SystemExit(f"cudaHostRegister of the shared host frame failed: {err}")
+            dist.barrier()
+            if rank == 0:
+                os.unlink(path[0])
+            job["shared"] = shared
+            job["out_img"] = shared[: size * size].view(size, size)
+            job["out_nrm"] = shared[size * size:].view(size, size) if dim == 3 else None
             ptr, nbytes = ctx.device_image()
             job["dev_img"] = torch.as_tensor(DevArray(ptr, size * size, "<i4"), device=f"cuda:{local}").view(size, size)
             if dim == 3:
@@ -326,14 +346,10 @@ def run_mine(args, workloads):
         else:
             if job["dim"] == 2:
                 ctx.render2D_host(job["cells"], None)
+                ctx.publish(2, job["out_img"].data_ptr())
             else:
                 ctx.render3D_host(job["cells"], None, None)
-            gather(job)
-            if rank == 0:           # the caller's device holds the frame; it alone hands it to the host
-                job["out_img"].copy_(job["dev_img"])
-                if job["dim"] == 3:
-                    job["out_nrm"].copy_(job["dev_nrm"])
-            torch.cuda.synchronize()
+                ctx.publish(3, job["out_img"].data_ptr(), job["out_nrm"].data_ptr())
         return (time.perf_counter() - t0) * 1e3
 
     def barrier():
@@ -359,6 +375,16 @@ def run_mine(args, workloads):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = sum(j["ctx"].stats().n_launches for j in jobs)
+    dev_digest = {}
+    if world > 1 and rank == 0:     # what the NCCL exchange left on rank 0's device after the last timed frame
+        for j in jobs:
+            d = {"image": digest(j["dev_img"].cpu().numpy())}
+            if j["dim"] == 3:
+                d["normals"] = digest(j["dev_nrm"].cpu().numpy().view(np.uint32))
+            dev_digest[f"{j['model']}_{j['dim']}d_{j['size']}"] = d
+        for j in jobs:              # the end-to-end frames must fill the host frame themselves
+            j["shared"].zero_()
+    barrier()
     for _ in range(min(args.warmup, 3)):
         step(frame_e2e)
     e2e = np.array([step(frame_e2e) for _ in range(args.steps)])         # [K, n_jobs] wall ms
@@ -378,7 +404,10 @@ def run_mine(args, workloads):
             got = {"image": digest(j["out_img"].numpy())}
             if j["dim"] == 3:
                 got["normals"] = digest(j["out_nrm"].numpy().view(np.uint32))
-            (verified if all(got[k] == want[k] for k in got) else mismatched).append(case)
+            ok = all(got[k] == want[k] for k in got)
+            if case in dev_digest:
+                ok = ok and all(dev_digest[case][k] == want[k] for k in got)
+            (verified if ok else mismatched).append(case)
 
     # BASELINE.json config 4 ("bear 3D heightmap + normals + SSAO"): mpr::Effects::drawSSAO / drawShaded on the
     # last 3D frame, host clock around the synchronised calls (the reference's GUI times them the same way,
@@ -464,6 +493,9 @@ def run_mine(args, workloads):
                        "wall_ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": j["wall_ms"] / args.steps for j in jobs},
                        "ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(dev[:, i].mean()) for i, j in enumerate(jobs)},
                        "e2e_ms_per_frame": {f"{j['model']}_{j['dim']}d_{j['size']}": float(e2e[:, i].mean()) for i, j in enumerate(jobs)},
+                       "e2e_protocol": ("host tape in, host frame out through mprb_render*_host (pinned buffers), wall clock" if world == 1 else
+                                        "host tape in on every rank; each rank stores the blocks it owns into ONE page-locked host frame "
+                                        "shared by the ranks (mprb_ctx_publish over its own PCIe link, no device-side gather); wall clock, max over ranks"),
                        "exchange_ms_per_frame_rank0": {f"{j['model']}_{j['dim']}d_{j['size']}": round(j.get("gather_ms", 0.0) / max(j.get("gather_n", 1), 1), 4) for j in jobs},
                        "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
                        "frame_stats": stats_one, "effects_ms": effects_ms},

@@ -104,6 +104,8 @@ typedef struct mprb_frame_stats {
     uint64_t f_items;         /* float-stage work items: runs of up to 2 (4) tiles that share one tape */
     uint64_t p_written;       /* arena cells actually written by pushes: sibling tiles whose verdicts
                                  agree share ONE copy of their shortened tape (p_kept counts it per tile) */
+    uint64_t i_sub_tiles;     /* of i_tiles: tiles of a small level evaluated clause-parallel, one warp per tile
+                                 on the plan written with the parent's shortened tape (k_eval_sub) */
 } mprb_frame_stats;
 
 /* ---- context: mpr::Context::Context(int32_t) (src/context.cpp:16-49) ------------ */
@@ -159,6 +161,14 @@ int mprb_render3d_heatmap(mprb_ctx* ctx, const mprb_tape* tape, const float mat4
 size_t mprb_exchange_bytes(const mprb_ctx* ctx, int dim);
 int mprb_exchange_pack(mprb_ctx* ctx, int dim, void* dst_device, void* stream);
 int mprb_exchange_unpack(mprb_ctx* ctx, int dim, const void* src_device, void* stream);
+/* Stores the 64x64-px blocks this context owns (all of them without sharding) of the frame last
+ * rendered straight into full-size images somewhere else: S*S int32 depth / filled values and, for
+ * dim = 3, S*S packed normals (null = skip).  The destinations may be page-locked host memory the
+ * device can address (cudaHostAlloc, or cudaHostRegister'ed pages - e.g. a shared-memory segment that
+ * the other ranks' processes registered too, so that N GPUs fill ONE host frame over N PCIe links at
+ * once and nobody gathers it on a device first), or memory of a peer device with access enabled.  One
+ * launch of stores on the context's stream; returns when they have landed. */
+int mprb_ctx_publish(mprb_ctx* ctx, int dim, int32_t* dst_image, uint32_t* dst_normals);
 
 /* ---- post-effects: mpr::Effects (inc/effects.hpp:21-37, src/effects.cu:229-297) ---- */
 typedef struct mprb_effects mprb_effects;

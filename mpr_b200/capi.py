@@ -13,7 +13,8 @@ from pathlib import Path
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libmprb.so"
+# MPRB_LIBRARY: another build of the library (A/B timing of two builds in one job); default = the in-tree one
+LIB_PATH = Path(os.environ["MPRB_LIBRARY"]) if os.environ.get("MPRB_LIBRARY") else _PKG / "libmprb.so"
 
 
 class TileNode(C.Structure):
@@ -68,6 +69,7 @@ class FrameStats(C.Structure):
         ("n_launches", C.c_int32),
         ("f_items", C.c_uint64),
         ("p_written", C.c_uint64),
+        ("i_sub_tiles", C.c_uint64),
     ]
 
     def asdict(self):
@@ -85,7 +87,7 @@ EXPORTS = [
     "mprb_render3d_host", "mprb_frame_stats_get", "mprb_tape_from_frep", "mprb_free", "mprb_free_device",
     "mprb_last_error", "mprb_version", "mprb_effects_create", "mprb_effects_destroy",
     "mprb_effects_draw_ssao", "mprb_effects_draw_shaded", "mprb_effects_buffers",
-    "mprb_malloc_managed", "mprb_exchange_bytes", "mprb_exchange_pack", "mprb_exchange_unpack", "mprb_render2d_brute", "mprb_render2d_heatmap", "mprb_render3d_heatmap",
+    "mprb_malloc_managed", "mprb_exchange_bytes", "mprb_exchange_pack", "mprb_exchange_unpack", "mprb_ctx_publish", "mprb_render2d_brute", "mprb_render2d_heatmap", "mprb_render3d_heatmap",
 ]
 
 _lib = None
@@ -132,6 +134,8 @@ def lib():
     L.mprb_exchange_bytes.restype = C.c_size_t
     L.mprb_exchange_pack.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p]
     L.mprb_exchange_unpack.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p]
+    if hasattr(L, "mprb_ctx_publish"):          # absent from older builds loaded through MPRB_LIBRARY
+        L.mprb_ctx_publish.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p]
     L.mprb_effects_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(vp)]
     L.mprb_effects_destroy.argtypes = [vp]
     L.mprb_effects_destroy.restype = None
@@ -330,6 +334,11 @@ class Context:
 
     def exchange_unpack(self, dim: int, src_ptr: int, stream: int = 0):
         _check(lib().mprb_exchange_unpack(self._h, dim, src_ptr, stream))
+
+    def publish(self, dim: int, image_ptr: int, normals_ptr: int = 0):
+        """Owned 64x64-px blocks of the last frame -> full-size images at these addresses (page-locked
+        host memory or a peer device's); mprb_ctx_publish."""
+        _check(lib().mprb_ctx_publish(self._h, dim, image_ptr, normals_ptr or None))
 
     def render2D_host(self, cells: np.ndarray, image_out: np.ndarray, mat=None, z: float = 0.0):
         m = mat_colmajor(np.eye(3) if mat is None else mat)

@@ -81,6 +81,7 @@ struct TapeDev {
     uint64_t* chunked = nullptr;     // the same tape in chunk-terminated layout (tape_stream.cuh)
     RootClause* sched = nullptr;     // clause-parallel plan for the root level (see k_eval_root)
     int32_t* level_start = nullptr;
+    uint16_t* prevw = nullptr;       // per clause: the value id its output slot held before it
     int32_t group = 0;               // threads per tile; 0 = no plan (serial root walk)
     int32_t smem_per_tile = 0;
 };
@@ -94,6 +95,7 @@ struct mprb_tape {
     int32_t n_slots = 0;
     std::vector<RootClause> sched;       // host copy of the root plan
     std::vector<int32_t> level_start;
+    std::vector<uint16_t> prevw;
     int32_t n_levels = 0;
     int32_t result_v = 0;
     mutable std::mutex mu;
@@ -129,6 +131,19 @@ struct mprb_ctx {
     uint64_t* stage_cells = nullptr; // pinned staging for host tapes
     int32_t stage_cells_cap = 0;
     bool serial_root = false;        // debugging / A-B switch: MPRB_SERIAL_ROOT=1
+    // Clause-parallel plans of the tapes k_eval_root shortens, for small levels (k_eval_sub)
+    int32_t* plans = nullptr;        // device: plan arena (32-bit words)
+    long long plans_words = 0;
+    int32_t* plan_of = nullptr;      // device: per level-0 tile, word offset of its plan or -1
+    long long plan_of_cap = 0;
+    int sub_waves = 4;               // k_eval_sub serves levels of up to this many waves of tiles; MPRB_SUB_WAVES (0 = off)
+    // What the last frame of (hint_tape, hint_dim) looked like: plans cost k_eval_root time and k_eval_sub a
+    // launch, so both are skipped while the level below the root is large or its tapes are too short to
+    // plan (looked at again every 32nd frame; the frame itself is the same either way).
+    const void* hint_tape = nullptr;
+    int hint_dim = 0;
+    int hint_parents = 0, hint_plans = 0;
+    unsigned frame_no = 0;
     int32_t* owned_tiles = nullptr;  // device: level-0 screen tiles (y * tiles_per_side + x) this context renders
     int n_owned = 0;
     unsigned long long* heat_units = nullptr;   // work meter of render*_heatmap (device, S*S), lazily allocated
@@ -208,6 +223,7 @@ std::vector<uint64_t> chunk_layout(const uint64_t* cells, int32_t n) {
 struct RootPlan {
     std::vector<RootClause> sched;
     std::vector<int32_t> level_start;
+    std::vector<uint16_t> prevw;      // [i] = value id that sat in clause i's output slot before it wrote there
     int result_v = 0;
 };
 
@@ -221,6 +237,7 @@ RootPlan build_root_plan(const uint64_t* cells, int32_t n_cells) {
     for (int k = 0; k < 3; ++k) if (ax[k]) writer[ax[k]] = 1 + k;
     std::vector<int> depth(n + 4, 0);
     std::vector<RootClause> byidx(n + 1);
+    p.prevw.assign(n + 1, 0);
     int n_choice = 0, max_depth = 0;
     for (int i = 1; i <= n; ++i) {
         const uint64_t d = cells[i];
@@ -234,11 +251,14 @@ RootPlan build_root_plan(const uint64_t* cells, int32_t n_cells) {
         const bool is_choice = op >= OP_MIN_LI && op <= OP_MAX_LR;
         const bool past_cap = is_choice && n_choice >= kMaxChoices;
         n_choice += is_choice;
-        rc.op_idx = op | (past_cap ? 0x100u : 0u) | (uint32_t(i) << 12);
+        // bits 9 / 10: the left / right operand's slot is the output slot (a verdict for it drops the clause)
+        rc.op_idx = op | (past_cap ? 0x100u : 0u) | (lhs == out ? 0x200u : 0u) | (rhs != 0 && rhs == out ? 0x400u : 0u) |
+                    (uint32_t(i) << 12);
         byidx[i] = rc;
         const int dep = 1 + std::max(depth[rc.lsrc], depth[rc.rsrc]);
         depth[3 + i] = dep;
         max_depth = std::max(max_depth, dep);
+        p.prevw[i] = uint16_t(std::min(writer[out], 0xffff));
         writer[out] = 3 + i;
     }
     p.result_v = writer[(uint32_t(cells[n + 1]) >> 8) & 0xff];
@@ -283,6 +303,7 @@ const TapeDev* tape_on(const mprb_tape* t, int device) {
         if (per_tile <= max_smem) {
             e = upload(&d.sched, t->sched);
             if (e == cudaSuccess) e = upload(&d.level_start, t->level_start);
+            if (e == cudaSuccess && n + 4 < 0xffff) e = upload(&d.prevw, t->prevw);
             d.group = group;
             d.smem_per_tile = per_tile;
         }
@@ -292,6 +313,7 @@ const TapeDev* tape_on(const mprb_tape* t, int device) {
         if (d.chunked) cudaFree(d.chunked);
         if (d.sched) cudaFree(d.sched);
         if (d.level_start) cudaFree(d.level_start);
+        if (d.prevw) cudaFree(d.prevw);
         fail(MPRB_E_CUDA, "tape upload to device %d: %s", device, cudaGetErrorString(e));
         return nullptr;
     }
@@ -412,6 +434,43 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         MPRB_CUDA(cudaMemsetAsync(heat_units, 0, sizeof(unsigned long long) * size_t(S) * S, s));
     }
 
+    // Small levels below the root run clause-parallel (k_eval_sub) on plans k_eval_root writes with the
+    // tapes it shortens.  A tile of that kernel gets a fixed slice of shared memory, sized for the root
+    // tape (no shortened tape needs more) but at most 24 KB; the level is "small" while its tiles make at
+    // most sub_waves waves of that kernel.
+    const bool clause_parallel_root = td->group > 0 && !c->serial_root && !heat && !brute;
+    int sub_slice = 0, sub_max_parents = 0, sub_grid = 0;
+    const bool hinted = c->hint_tape == static_cast<const void*>(plan) && c->hint_dim == dim && c->sub_waves < 100000 &&
+                        (c->frame_no++ & 31u) != 31u;
+    if (clause_parallel_root && c->sub_waves > 0 && n_levels >= 2 && td->prevw && plan->n_levels < 256) {
+        const int need = sub_need_bytes(n_cells - 2 + 4, plan->n_levels);
+        sub_slice = std::min(std::max((need + 15) / 16 * 16, 2048), 24576);
+        const int warps = sub_warps(sub_slice);
+        const int ctas = (2 * (warps * sub_slice + 1024) <= 227 * 1024) ? 2 : 1;
+        sub_grid = c->sm_count * ctas;
+        sub_max_parents = std::max(1, c->sub_waves * sub_grid * warps / 64);
+        if (hinted && (c->hint_parents > 2 * sub_max_parents || c->hint_plans == 0)) sub_slice = 0;
+    }
+    if (sub_slice) {
+        const long long per_plan = kPlanHeader + plan->n_levels + 4 + 4LL * (sub_slice / 10 + 1);
+        // never more plans than root tiles; the arena running out only sends tiles to the serial kernel
+        const long long want = std::min<long long>(per_plan * (std::min<long long>(sub_max_parents, count0) + 8), 64LL << 20);
+        if (c->plans_words < want) {
+            if (c->plans) cudaFree(c->plans);
+            c->plans = nullptr;
+            c->plans_words = 0;
+            MPRB_CUDA(cudaMalloc(&c->plans, sizeof(int32_t) * size_t(want)));
+            c->plans_words = want;
+        }
+        if (c->plan_of_cap < count0) {
+            if (c->plan_of) cudaFree(c->plan_of);
+            c->plan_of = nullptr;
+            c->plan_of_cap = 0;
+            MPRB_CUDA(cudaMalloc(&c->plan_of, sizeof(int32_t) * size_t(count0)));
+            c->plan_of_cap = count0;
+        }
+    }
+
     int q = 0;
     const int small_grid = c->sm_count * 4;
     const int group = float_group(n_slots, heat);      // tiles per work item of the float pass
@@ -460,7 +519,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         ea.heat = heat_units;
         ea.heat_px = px_of[l];
         ea.n_root = n_cells - 2;
-        if (root && td->group > 0 && !c->serial_root && !heat) {
+        if (root && clause_parallel_root) {
             EvalRootArgs ra = {};
             ra.arena = c->arena;
             ra.tape_index = &c->ctl->tape_cursor;
@@ -484,8 +543,45 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
             ra.group = td->group;
             ra.smem_per_tile = td->smem_per_tile;
             ra.z = z;
+            if (sub_slice) {
+                ra.plans = c->plans;
+                ra.plan_cursor = &c->ctl->plan_cursor;
+                ra.plan_cap = int32_t(std::min<long long>(c->plans_words, INT32_MAX));
+                ra.plan_of = c->plan_of;
+                ra.sub_slice = sub_slice;
+                ra.plan_count = &c->ctl->plan_count;
+                ra.max_plans = sub_max_parents;
+                ra.plan_min = c->sub_waves >= 100000 ? 0 : kPlanMinClauses;     // the test setting plans everything
+                ra.prevw = td->prevw;
+            }
             launch_eval_root(dim, ra, mat, s);
         } else {
+            if (l == 1 && sub_slice) {
+                // tiles whose parent carries a plan, when the level is small; the serial kernel skips those
+                EvalSubArgs sa = {};
+                sa.arena = c->arena;
+                sa.tape_index = &c->ctl->tape_cursor;
+                sa.arena_cap = int32_t(c->arena_cells);
+                sa.image = c->filled[st];
+                sa.tiles = c->tiles[st];
+                sa.tiles_cap = ea.tiles_cap;
+                sa.tps = uint32_t(tps);
+                sa.ptiles = ea.ptiles;
+                sa.pactive = ea.pactive;
+                sa.n_parents = ea.n_parents;
+                sa.ptps = ea.ptps;
+                sa.ctl = c->ctl;
+                sa.queue = &c->ctl->queue[q++];
+                sa.level = l;
+                sa.plans = c->plans;
+                sa.plan_of = c->plan_of;
+                sa.slice = sub_slice;
+                sa.max_parents = sub_max_parents;
+                sa.z = z;
+                launch_eval_sub(dim, sa, mat, sub_grid, s);
+                ea.plan_of = c->plan_of;
+                ea.sub_max_parents = sub_max_parents;
+            }
             int grid = c->sm_count * cached_occupancy(c, 0, dim, root, n_slots);
             if (root) {
                 const long long items = (count0 + 31) / 32;
@@ -567,6 +663,8 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         tm.mark();
     }
     c->stats.n_launches = tm.n - 1;
+    c->hint_tape = plan;
+    c->hint_dim = dim;
     MPRB_CUDA(cudaGetLastError());
     return MPRB_OK;
 }
@@ -647,6 +745,7 @@ int finish(mprb_ctx* c, int dim) {
         a.f_cells += b.f_cells;
         a.f_items += b.f_items;
         a.p_written += b.p_written;
+        a.i_sub_tiles += b.i_sub_tiles;
         a.n_pixels += b.n_pixels;
         a.n_cells += b.n_cells;
         a.overflow |= b.overflow;
@@ -678,7 +777,10 @@ int finish_one(mprb_ctx* c, int dim) {
     st.n_cells = f.stats[ST_N_CELLS];
     st.f_items = f.stats[ST_F_ITEMS];
     st.p_written = f.stats[ST_P_WRITTEN];
+    st.i_sub_tiles = f.stats[ST_I_SUB];
     st.overflow = f.overflow;
+    c->hint_parents = f.n_active[0];
+    c->hint_plans = f.plan_count;
     cudaEventElapsedTime(&st.gpu_ms, c->ev_begin, c->ev_end);
     if (c->timing) {
         for (int i = 0; i < n_launches && i < kMaxLaunches; ++i)
@@ -789,6 +891,7 @@ static int create_one(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx
     c->size = image_size_px;
     const int tps0 = image_size_px / 64;
     c->serial_root = getenv("MPRB_SERIAL_ROOT") != nullptr;
+    if (const char* e = getenv("MPRB_SUB_WAVES")) c->sub_waves = std::max(0, atoi(e));
     c->row_begin = opts ? opts->row_begin : 0;
     c->row_end = (opts && opts->row_end > 0) ? opts->row_end : tps0;
     c->row_mod = (opts && opts->row_mod > 1) ? opts->row_mod : 1;
@@ -896,6 +999,8 @@ void mprb_ctx_destroy(mprb_ctx* c) {
     if (c->stage_cells) cudaFreeHost(c->stage_cells);
     if (c->heat_units) cudaFree(c->heat_units);
     if (c->owned_tiles) cudaFree(c->owned_tiles);
+    if (c->plans) cudaFree(c->plans);
+    if (c->plan_of) cudaFree(c->plan_of);
     if (c->host_plan) mprb_tape_destroy(c->host_plan);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -952,6 +1057,7 @@ int mprb_tape_create(const uint64_t* host_cells, int32_t n_cells, mprb_tape** ou
             t->result_v = plan.result_v;
             t->sched.swap(plan.sched);
             t->level_start.swap(plan.level_start);
+            t->prevw.swap(plan.prevw);
         }
     }
     // Device-side copies are made per device on first use (tape_on); make the current device's now
@@ -977,6 +1083,7 @@ void mprb_tape_destroy(mprb_tape* t) {
         if (d.chunked) cudaFree(d.chunked);
         if (d.sched) cudaFree(d.sched);
         if (d.level_start) cudaFree(d.level_start);
+        if (d.prevw) cudaFree(d.prevw);
     }
     cudaSetDevice(cur);
     if (t->cells) cudaFree(t->cells);
@@ -1066,6 +1173,39 @@ int mprb_render3d_host(mprb_ctx* c, const uint64_t* host_cells, int32_t n_cells,
     if (normals_out)
         MPRB_CUDA(cudaMemcpyAsync(normals_out, c->normals, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
     return finish(c, 3);
+}
+
+// Address a kernel on `device` may store through for `p`, or null: device / managed memory as it is,
+// page-locked host memory by its mapping.
+static void* device_address(void* p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes at = {};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return p;
+    if (at.type == cudaMemoryTypeHost) return at.devicePointer;
+    return nullptr;
+}
+
+int mprb_ctx_publish(mprb_ctx* c, int dim, int32_t* dst_image, uint32_t* dst_normals) {
+    if (!c) return fail(MPRB_E_ARG, "null context");
+    if (dim != 2 && dim != 3) return fail(MPRB_E_ARG, "dim must be 2 or 3");
+    if (!c->peers.empty()) return fail(MPRB_E_ARG, "a multi-GPU context holds its whole frame on the primary device");
+    const int tiles = c->size / 64;
+    const int world = std::max(c->row_mod, 1);
+    if (c->row_begin != 0 || c->row_end != tiles || (world > 1 && c->col_step != 1))
+        return fail(MPRB_E_ARG, "publish needs the tile-cyclic sharding (col_step = 1) over the whole frame, or none");
+    MPRB_CUDA(cudaSetDevice(c->device));
+    int32_t* const d_img = static_cast<int32_t*>(device_address(dst_image));
+    uint32_t* const d_nrm = dim == 3 && dst_normals ? static_cast<uint32_t*>(device_address(dst_normals)) : nullptr;
+    if (!d_img || (dim == 3 && dst_normals && !d_nrm))
+        return fail(MPRB_E_ARG, "destination is neither device memory nor page-locked host memory (cudaHostRegister it)");
+    launch_publish(c->size, world, c->row_rem, d_nrm ? 3 : 2, c->filled[3], c->normals, d_img, d_nrm, c->stream);
+    MPRB_CUDA(cudaGetLastError());
+    MPRB_CUDA(cudaStreamSynchronize(c->stream));
+    return MPRB_OK;
 }
 
 static int exchange_check(const mprb_ctx* c, int dim) {

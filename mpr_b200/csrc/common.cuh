@@ -48,6 +48,7 @@ enum : int {
     ST_N_CELLS = 18,   // normal-pass cells visited, summed over pixels
     ST_F_ITEMS = 19,   // float-stage work items (runs of tiles sharing a tape, walked together)
     ST_P_WRITTEN = 20, // arena cells actually written by pushes (tiles with equal verdicts share one tape)
+    ST_I_SUB = 21,     // interval tiles evaluated clause-parallel by k_eval_sub (part of ST_I_TILES)
     ST_COUNT = 22,
 };
 
@@ -59,6 +60,8 @@ struct FrameCtl {
     int32_t queue[10];     // work-queue heads, one per persistent launch
     int32_t overflow;      // bit i set: tile array of stage i+1 too small
     int32_t tape_cursor;   // arena allocation cursor in cells (the reference's *tape_index)
+    int32_t plan_cursor;   // plan arena allocation cursor in words (k_eval_root -> k_eval_sub)
+    int32_t plan_count;    // plans written so far (capped: only small levels use them)
     unsigned long long stats[ST_COUNT];
 };
 

@@ -304,6 +304,8 @@ k_eval_tiles(const EvalTilesArgs a, const typename MatOf<DIM>::type mat)
             inband = (sy >= a.row_begin) && (sy < a.row_end) && ((sy + a.col_step * sx) % a.row_mod == a.row_rem);
         } else {
             const int rank = item >> 1;
+            // a small level: parents with a clause-parallel plan belong to k_eval_sub
+            if (a.plan_of && (n_items >> 1) <= a.sub_max_parents && a.plan_of[a.pactive[rank]] >= 0) continue;
             // 3D: the upper half of the children (z = 2, 3) goes first, for the same reason
             const int sub = DIM == 3 ? ((((item & 1) ^ 1) << 5) | lane) : (((item & 1) << 5) | lane);
             const TileNode parent = a.ptiles[a.pactive[rank]];
@@ -720,6 +722,43 @@ __device__ __forceinline__ void group_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// One clause of a clause-parallel plan (k_eval_root, k_eval_sub): the interval operations of the serial
+// walk (context.cu:223-287), operands already fetched; c = the min / max verdict.
+__device__ __forceinline__ ival eval_plan_clause(uint32_t op, const ival Lv, const ival Rv, float imm, int& c) {
+    ival o;
+    switch (op) {
+        case OP_SQUARE: o = iv_square(Lv); break;
+        case OP_SQRT:   o = iv_sqrt(Lv); break;
+        case OP_NEG:    o = iv_neg(Lv); break;
+        case OP_SIN:    o = iv_sin(Lv); break;
+        case OP_COS:    o = iv_cos(Lv); break;
+        case OP_ASIN:   o = iv_asin(Lv); break;
+        case OP_ACOS:   o = iv_acos(Lv); break;
+        case OP_ATAN:   o = iv_atan(Lv); break;
+        case OP_EXP:    o = iv_exp(Lv); break;
+        case OP_ABS:    o = iv_abs(Lv); break;
+        case OP_LOG:    o = iv_log(Lv); break;
+        case OP_ADD_LI: o = iv_add(Lv, imm); break;
+        case OP_ADD_LR: o = iv_add(Lv, Rv); break;
+        case OP_MUL_LI: o = iv_mul(Lv, imm); break;
+        case OP_MUL_LR: o = iv_mul(Lv, Rv); break;
+        case OP_MIN_LI: o = iv_min(Lv, iv(imm, imm), c); break;
+        case OP_MIN_LR: o = iv_min(Lv, Rv, c); break;
+        case OP_MAX_LI: o = iv_max(Lv, iv(imm, imm), c); break;
+        case OP_MAX_LR: o = iv_max(Lv, Rv, c); break;
+        case OP_SUB_LI: o = iv_sub(Lv, imm); break;
+        case OP_SUB_IR: o = iv_sub(imm, Rv); break;
+        case OP_SUB_LR: o = iv_sub(Lv, Rv); break;
+        case OP_DIV_LI: o = iv_div(Lv, imm); break;
+        case OP_DIV_IR: o = iv_div(imm, Rv); break;
+        case OP_DIV_LR: o = iv_div(Lv, Rv); break;
+        case OP_COPY_IMM: o = iv(imm, imm); break;
+        case OP_COPY_RHS: o = Rv; break;
+        default: o = Lv; break;                      // OP_COPY_LHS
+    }
+    return o;
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(kRootThreads)
 k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
@@ -749,6 +788,7 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
     // Occlusion pre-mask.  The image changes under us (other tiles' atomicMax), so one
     // thread looks and the whole group follows its answer.
     if (t == 0) {
+        if (a.plans) a.plan_of[tile] = -1;
         bool al = (sy >= a.row_begin) && (sy < a.row_end) && ((sy + a.col_step * sx) % a.row_mod == a.row_rem);
         if (DIM == 3 && al && __ldcg(&a.image[img_index]) > sz) al = false;
         scratch[12] = al;
@@ -791,46 +831,28 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
     group_sync(bar, G);
 
     // ---- forward: one dependency level at a time ---------------------------------------
+    // Level bounds and the first clause of each thread are fetched (L2) two and one levels ahead: the
+    // levels are short, and a chain of dependent global loads per level would cost more than the level.
     bool any_choice = false;
-    for (int L = 0; L < a.n_levels; ++L) {
-        const int k_end = a.level_start[L + 1];
-        for (int k = a.level_start[L] + t; k < k_end; k += G) {
-            const RootClause rc = a.sched[k];
+    const int32_t* __restrict__ const ls = a.level_start;
+    const int nl = a.n_levels;
+    int k0 = ls[0], k1 = ls[1], k2 = ls[min(2, nl)];
+    RootClause nxt = {};
+    if (k0 + t < k1) nxt = a.sched[k0 + t];
+    for (int L = 0; L < nl; ++L) {
+        const int k_end = k1;
+        RootClause rc = nxt;
+        const int k3 = ls[min(L + 3, nl)];
+        if (k1 + t < k2) nxt = a.sched[k1 + t];
+        for (int k = k0 + t; k < k_end; k += G) {
+            if (k >= k0 + G) rc = a.sched[k];
             const uint32_t op = rc.op_idx & 0xff;
             const uint32_t idx = rc.op_idx >> 12;
             const float imm = rc.imm;
             const ival Lv = V[rc.lsrc];
             const ival Rv = V[rc.rsrc];
-            ival o;
             int c = 0;
-            switch (op) {
-                case OP_SQUARE: o = iv_square(Lv); break;
-                case OP_SQRT:   o = iv_sqrt(Lv); break;
-                case OP_NEG:    o = iv_neg(Lv); break;
-                case OP_SIN:    o = iv_sin(Lv); break;
-                case OP_COS:    o = iv_cos(Lv); break;
-                case OP_ASIN:   o = iv_asin(Lv); break;
-                case OP_ACOS:   o = iv_acos(Lv); break;
-                case OP_ATAN:   o = iv_atan(Lv); break;
-                case OP_EXP:    o = iv_exp(Lv); break;
-                case OP_ABS:    o = iv_abs(Lv); break;
-                case OP_LOG:    o = iv_log(Lv); break;
-                case OP_ADD_LI: o = iv_add(Lv, imm); break;
-                case OP_ADD_LR: o = iv_add(Lv, Rv); break;
-                case OP_MUL_LI: o = iv_mul(Lv, imm); break;
-                case OP_MUL_LR: o = iv_mul(Lv, Rv); break;
-                case OP_MIN_LI: o = iv_min(Lv, iv(imm, imm), c); break;
-                case OP_MIN_LR: o = iv_min(Lv, Rv, c); break;
-                case OP_MAX_LI: o = iv_max(Lv, iv(imm, imm), c); break;
-                case OP_MAX_LR: o = iv_max(Lv, Rv, c); break;
-                case OP_SUB_LI: o = iv_sub(Lv, imm); break;
-                case OP_SUB_IR: o = iv_sub(imm, Rv); break;
-                case OP_SUB_LR: o = iv_sub(Lv, Rv); break;
-                case OP_DIV_LI: o = iv_div(Lv, imm); break;
-                case OP_DIV_IR: o = iv_div(imm, Rv); break;
-                case OP_DIV_LR: o = iv_div(Lv, Rv); break;
-                default: o = Lv; break;
-            }
+            const ival o = eval_plan_clause(op, Lv, Rv, imm, c);
             V[3 + idx] = o;
             if (op >= OP_MIN_LI && op <= OP_MAX_LR) {
                 any_choice |= (c != 0);
@@ -839,6 +861,9 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
                 C[idx] = (rc.op_idx & 0x100u) ? 0 : uint8_t(c);
             }
         }
+        k0 = k1;
+        k1 = k2;
+        k2 = k3;
         group_sync(bar, G);
     }
     if (any_choice) scratch[0] = 1;                          // benign same-value race
@@ -872,23 +897,40 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
 
     if (pushing) {
         // ---- mark: result -> operands, top level first ------------------------------------
+        // KS[k] = clause at schedule position k stays in the shortened tape (the values are done with,
+        // the flags take the last eighth of their room; a clause's liveness is final when its level is swept)
+        uint8_t* const KS = mine + size_t(nv) * 6;
         if (t == 0) A[a.result_v] = 1;
         group_sync(bar, G);
-        for (int L = a.n_levels - 1; L >= 0; --L) {
-            const int k_end = a.level_start[L + 1];
-            for (int k = a.level_start[L] + t; k < k_end; k += G) {
-                const RootClause rc = a.sched[k];
-                const uint32_t op = rc.op_idx & 0xff;
-                const uint32_t idx = rc.op_idx >> 12;
-                if (!A[3 + idx]) continue;
-                const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[idx] : 0;
-                if (c == 0) { A[rc.lsrc] = 1; A[rc.rsrc] = 1; }
-                else if (c == 1) { A[rc.lsrc] = 1; }
-                else { A[rc.rsrc] = 1; }                     // rsrc == 0 for immediate forms
+        {
+            int e1 = ls[nl], e0 = ls[nl - 1], em = ls[max(nl - 2, 0)];      // level L is [e0, e1), level L - 1 [em, e0)
+            RootClause ahead = {};
+            if (e0 + t < e1) ahead = a.sched[e0 + t];
+            for (int L = nl - 1; L >= 0; --L) {
+                RootClause rc = ahead;
+                const int emm = ls[max(L - 2, 0)];
+                if (L > 0 && em + t < e0) ahead = a.sched[em + t];
+                for (int k = e0 + t; k < e1; k += G) {
+                    if (k >= e0 + G) rc = a.sched[k];
+                    const uint32_t op = rc.op_idx & 0xff;
+                    const uint32_t idx = rc.op_idx >> 12;
+                    if (!A[3 + idx]) { KS[k] = 0; continue; }
+                    const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[idx] : 0;
+                    // in the shortened tape unless the verdict's operand already sits in the output slot
+                    KS[k] = ((c == 1 && (rc.op_idx & 0x200u)) || (c == 2 && (rc.op_idx & 0x400u))) ? 0 : 1;
+                    if (c == 0) { A[rc.lsrc] = 1; A[rc.rsrc] = 1; }
+                    else if (c == 1) { A[rc.lsrc] = 1; }
+                    else { A[rc.rsrc] = 1; }                     // rsrc == 0 for immediate forms
+                }
+                e1 = e0;
+                e0 = em;
+                em = emm;
+                group_sync(bar, G);
             }
-            group_sync(bar, G);
         }
         // ---- sweep: compact kept clauses in tape order ---------------------------------------
+        // (a live min / max whose verdict names an operand already sitting in the output slot is dropped,
+        // context.cu:404-447)
         const int per = (n + G - 1) / G;
         const int i_begin = 1 + t * per, i_end = min(n + 1, i_begin + per);
         int kept = 0;
@@ -921,6 +963,12 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
         // cells at offsets 1..62 between a back link (cell 0) and a forward link (cell 63).
         const int n_logical = total + 2;
         const int n_chunks = n_logical <= kChunk ? 1 : 1 + (n_logical - 63 + 61) / 62;
+        // A plan for k_eval_sub goes with the tape when it is small enough for that kernel's per-tile
+        // shared memory and the level can still turn out small (max_plans parents at most).
+        const int plan_nv = 4 + total;
+        const int plan_words = kPlanHeader + ((a.n_levels + 1 + 3) & ~3) + 4 * total;
+        const bool plan_fits = a.plans != nullptr && total <= kPlanMaxClauses && total >= a.plan_min && nv >= 4 * G + 8 &&
+                               sub_need_bytes(plan_nv, a.n_levels) <= a.sub_slice;
         if (t == 0) {
             const int need = n_chunks * kChunk;
             int base = -1;
@@ -929,9 +977,21 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
                 if (base + need >= a.arena_cap) base = -1;     // arena exhausted: keep the root tape
             }
             scratch[3] = base;
+            int pb = -1;
+            if (plan_fits && base >= 0 && *(volatile int32_t*)a.plan_count < a.max_plans &&
+                atomicAdd(a.plan_count, 1) < a.max_plans) {
+                pb = atomicAdd(a.plan_cursor, plan_words);
+                if (pb + plan_words > a.plan_cap) pb = -1;
+            }
+            scratch[13] = pb;
         }
         group_sync(bar, G);
         const int base = scratch[3];
+        const int pb = scratch[13];
+        // N[v] = value id in the shortened tape's plan (3 + its cell number), kNotInTape for a live clause
+        // that was dropped; the values themselves are done with, N takes their place.
+        uint32_t* const N = reinterpret_cast<uint32_t*>(mine);
+        constexpr uint32_t kNotInTape = 0xffffffffu;
         if (base >= 0) {
             int q = 1 + offset;
             for (int i = i_begin; i < i_end; ++i) {
@@ -940,14 +1000,20 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
                 const uint32_t w = uint32_t(d);
                 const uint32_t op = w & 0xff, i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
                 const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[i] : 0;
+                bool dropped = false;
                 if (c == 1) {
-                    if (i_lhs == i_out) continue;
+                    if (i_lhs == i_out) dropped = true;
                     d = (d & ~0xffull) | OP_COPY_LHS;
                 } else if (c == 2) {
-                    if (i_rhs != 0 && i_rhs == i_out) continue;
+                    if (i_rhs != 0 && i_rhs == i_out) dropped = true;
                     d = (d & ~0xffull) | (i_rhs ? OP_COPY_RHS : OP_COPY_IMM);
                 }
+                if (dropped) {
+                    if (pb >= 0) N[3 + i] = kNotInTape;
+                    continue;
+                }
                 arena[base + chunked_index(q, n_logical)] = d;
+                if (pb >= 0) N[3 + i] = uint32_t(3 + q);
                 ++q;
             }
             if (t == 0) {
@@ -967,6 +1033,109 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
             atomicAdd(&a.ctl->stats[ST_P_KEPT], written);
             atomicAdd(&a.ctl->stats[ST_P_WRITTEN], written);
         }
+        if (pb >= 0) {
+            // ---- the shortened tape's plan: its clauses in (level, opcode) order, renumbered ------------
+            // An operand of a kept clause names a root clause that may have left the tape: a dropped min / max
+            // (the value is then the one its output slot already held), or - for the operand a verdict
+            // made unused - anything at all.  A later backward walk of the shortened tape still marks that
+            // unused operand's SLOT (context.cu:386-402 looks at the slot bytes, not the opcode), which keeps
+            // alive whatever kept clause wrote the slot last.  Both cases are one question: which clause of
+            // the shortened tape wrote this slot last?  P[i] = the value that sat in clause i's output slot
+            // before it (host-built, api.cu); following it from the operand's root producer answers it.
+            uint16_t* const P = reinterpret_cast<uint16_t*>(mine + size_t(nv) * 4);
+            for (int i = t; i <= n; i += G) P[i] = a.prevw[i];
+            if (t < 4) N[t] = uint32_t(t);                                // none, x, y, z
+            group_sync(bar, G);                                           // N, P complete
+            auto in_tape = [&](uint32_t p) { return A[p] && N[p] != kNotInTape; };
+            // Slots are reused hundreds of times and most of their writers are dead in any one tile:
+            // pointer jumping first (P[i] skips writers that left the tape; log2(chain) rounds), so that a
+            // lookup is a hop or two.  In-place is safe: P[i] only ever moves to an earlier writer of the same
+            // slot with nothing kept in between, whichever of a neighbour's old / new value it reads.
+            for (;;) {
+                if (t == 0) scratch[14] = 0;
+                group_sync(bar, G);
+                bool moved = false;
+                for (int i = 1 + t; i <= n; i += G) {
+                    const uint32_t p = P[i];
+                    if (p > 3u && !in_tape(p)) {
+                        P[i] = P[p - 3u];
+                        moved = true;
+                    }
+                }
+                if (moved) scratch[14] = 1;
+                group_sync(bar, G);
+                const bool again = scratch[14] != 0;
+                group_sync(bar, G);
+                if (!again) break;
+            }
+            auto in_plan = [&](uint32_t p) -> uint32_t {                  // root value id -> plan value id
+                while (p > 3u && !in_tape(p)) p = P[p - 3u];
+                return N[p];
+            };
+            const int k_begin = min(n, t * per), k_end = min(n, k_begin + per);
+            int cnt = 0;
+            for (int k = k_begin; k < k_end; ++k) cnt += KS[k];
+            int pin = cnt;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(kFull, pin, o);
+                if ((t & 31) >= o) pin += v;
+            }
+            if ((t & 31) == 31) wsum[t >> 5] = pin;
+            group_sync(bar, G);
+            int pp = pin - cnt;
+            for (int wv = 0; wv < (t >> 5); ++wv) pp += wsum[wv];
+            int* const PP = reinterpret_cast<int*>(mine + ((size_t(nv) * 7 + 3) & ~size_t(3)));   // entries before each thread's range
+            PP[t] = pp;
+            int32_t* const hdr = a.plans + pb;
+            int32_t* const pls = hdr + kPlanHeader;
+            const int sched_off = kPlanHeader + ((a.n_levels + 1 + 3) & ~3);
+            RootClause* const out = reinterpret_cast<RootClause*>(hdr + sched_off);
+            for (int k = k_begin; k < k_end; ++k) {
+                if (!KS[k]) continue;
+                const RootClause rc = a.sched[k];
+                const uint32_t op = rc.op_idx & 0xff;
+                const uint32_t idx = rc.op_idx >> 12;
+                const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[idx] : 0;
+                RootClause e;
+                e.imm = rc.imm;
+                if (c == 0) {
+                    e.op_idx = op;
+                    e.lsrc = in_plan(rc.lsrc);
+                    e.rsrc = in_plan(rc.rsrc);
+                } else if (c == 1 || rc.rsrc != 0) {      // the chosen operand passes through, the other is only marked
+                    e.op_idx = OP_COPY_LHS;
+                    e.lsrc = in_plan(c == 1 ? rc.lsrc : rc.rsrc);
+                    e.rsrc = in_plan(c == 1 ? rc.rsrc : rc.lsrc);
+                } else {
+                    e.op_idx = OP_COPY_IMM;
+                    e.lsrc = in_plan(rc.lsrc);
+                    e.rsrc = 0;
+                }
+                e.op_idx |= (N[3 + idx] - 3u) << 12;
+                out[pp++] = e;
+            }
+            group_sync(bar, G);                                           // PP complete
+            for (int L = t; L < a.n_levels; L += G) {                     // where each level starts in the plan
+                const int ks = a.level_start[L];
+                const int owner = ks / per;
+                int v = PP[owner];
+                for (int k = owner * per; k < ks; ++k) v += KS[k];
+                pls[L] = v;
+            }
+            if (t == 0) {
+                pls[a.n_levels] = total;
+                hdr[PL_N] = total;
+                hdr[PL_LEVELS] = a.n_levels;
+                hdr[PL_RESULT] = int32_t(in_plan(uint32_t(a.result_v)));
+                hdr[PL_TAPE] = base;
+                hdr[PL_LOGICAL] = n_logical;
+                hdr[PL_VALUES] = plan_nv;
+                hdr[PL_SCHED] = sched_off;
+                hdr[PL_COUNT] = total;
+                a.plan_of[tile] = pb;
+            }
+        }
     }
     if (t == 0) {
         a.tiles[tile].position = out_position;
@@ -974,6 +1143,304 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
         a.tiles[tile].next = -1;
         atomicAdd(&a.ctl->stats[ST_I_TILES], 1ull);
         atomicAdd(&a.ctl->stats[ST_I_CELLS], (unsigned long long)n);
+    }
+}
+
+////////////////////////////////////////////////////////////////////////////////
+// Small levels below the root, evaluated clause-parallel.
+//
+// A level with few tiles (a small frame, or one GPU's share of a frame split eight ways) leaves
+// k_eval_tiles with a handful of warps, each walking a long tape one clause at a time: the frame
+// waits on a dependent chain, not on the machine.  The tapes of such a level were all shortened by
+// k_eval_root, which knows their dependency levels (a subset of the root tape's), so it writes a plan
+// next to each tape (EvalRootArgs::plans) and here ONE WARP owns one tile and runs the plan a level
+// at a time - the same scheme, values and verdicts as k_eval_root, with __syncwarp for a barrier.
+// Interval results do not depend on evaluation order, so the tile's classification and its
+// shortened tape (mark and sweep in tape order, written as a contiguous run like k_eval_root's)
+// are those of the serial walk (context.cu:188-459).
+//
+// Which kernel takes a tile is a function of device-side facts both kernels read the same way:
+// the level's parent count against max_parents, and whether the parent carries a plan.
+
+constexpr int kSubThreads = kSubMaxWarps * 32;
+
+template <int DIM>
+__global__ void __launch_bounds__(kSubThreads)
+k_eval_sub(const EvalSubArgs a, const typename MatOf<DIM>::type mat)
+{
+    extern __shared__ __align__(16) unsigned char s_sub[];
+    const int n_parents = min(*a.n_parents, a.tiles_cap / 64);
+    if (n_parents > a.max_parents) return;
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    unsigned char* const mine = s_sub + size_t(warp) * a.slice;
+    uint64_t* const arena = a.arena;
+    const uint32_t tps = a.tps;
+    const int n_items = n_parents * 64;
+    unsigned long long st_tiles = 0, st_cells = 0, st_ptiles = 0, st_pcells = 0, st_kept = 0;
+
+    for (;;) {
+        const int item = warp_next(a.queue);
+        if (item >= n_items) break;
+        const int rank = item >> 6;
+        const int sub = DIM == 3 ? 63 - (item & 63) : (item & 63);      // 3D: highest z first
+        const int pidx = a.pactive[rank];
+        const int plan = a.plan_of[pidx];
+        if (plan < 0) continue;                                          // k_eval_tiles has this parent
+        const TileNode parent = a.ptiles[pidx];
+        const int tile_index = rank * 64 + sub;
+        int sx, sy, sz = 0;
+        {
+            const int pp = parent.position;
+            const int px = pp % a.ptps, py = (pp / a.ptps) % a.ptps;
+            if (DIM == 3) {
+                const int pz = (pp / a.ptps) / a.ptps;
+                sx = px * 4 + (sub & 3);
+                sy = py * 4 + ((sub >> 2) & 3);
+                sz = pz * 4 + (sub >> 4);
+            } else {
+                sx = px * 8 + (sub & 7);
+                sy = py * 8 + (sub >> 3);
+            }
+        }
+        const int position = sx + sy * tps + (DIM == 3 ? sz * tps * tps : 0);
+        const int img_index = sx + sy * tps;
+
+        // Occlusion pre-mask: lane 0 looks, the warp follows
+        if (DIM == 3) {
+            int seen = 0;
+            if (lane == 0) seen = __ldcg(&a.image[img_index]);
+            seen = __shfl_sync(kFull, seen, 0);
+            if (seen > sz) {
+                if (lane == 0) {
+                    a.tiles[tile_index].position = -1;
+                    a.tiles[tile_index].tape = parent.tape;
+                    a.tiles[tile_index].next = -1;
+                }
+                continue;
+            }
+        }
+
+        const int32_t* const hdr = a.plans + plan;
+        const int n = hdr[PL_N], n_levels = hdr[PL_LEVELS], result_v = hdr[PL_RESULT];
+        const int ptape = hdr[PL_TAPE], p_logical = hdr[PL_LOGICAL], nv = hdr[PL_VALUES];
+        const RootClause* __restrict__ const sched = reinterpret_cast<const RootClause*>(hdr + hdr[PL_SCHED]);
+        float2* const V = reinterpret_cast<float2*>(mine);
+        uint8_t* const C = mine + size_t(nv) * 8;
+        uint8_t* const A = C + nv;
+        uint8_t* const LV = A + nv;                                      // dependency level of each value
+        int* const LS = reinterpret_cast<int*>(mine + ((nv * 11 + 3) & ~3));
+
+        __syncwarp();                                                    // the previous tile is done with `mine`
+        if (lane == 0) {                                                 // tile box -> axis intervals
+            const float ftps = float(tps);
+            const ival ix = iv(tile_edge(sx, ftps), tile_edge(sx + 1, ftps));
+            const ival iy = iv(tile_edge(sy, ftps), tile_edge(sy + 1, ftps));
+            const float* m = mat.d;
+            if (DIM == 3) {
+                const ival iz = iv(tile_edge(sz, ftps), tile_edge(sz + 1, ftps));
+                ival r[4];
+                #pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    r[i] = iv_add(iv_add(iv_add(iv_mul(ix, m[i]), iv_mul(iy, m[4 + i])), iv_mul(iz, m[8 + i])), m[12 + i]);
+                V[1] = iv_div(r[0], r[3]);
+                V[2] = iv_div(r[1], r[3]);
+                V[3] = iv_div(r[2], r[3]);
+            } else {
+                ival r[3];
+                #pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    r[i] = iv_add(iv_add(iv_mul(ix, m[i]), iv_mul(iy, m[3 + i])), m[6 + i]);
+                V[1] = iv_div(r[0], r[2]);
+                V[2] = iv_div(r[1], r[2]);
+                V[3] = iv(a.z, a.z);
+            }
+            V[0] = iv(0.0f, 0.0f);
+        }
+        for (int i = lane; i < nv; i += 32) A[i] = 0;
+        for (int i = lane; i <= n_levels; i += 32) LS[i] = hdr[kPlanHeader + i];
+        __syncwarp();
+
+        // ---- forward: one dependency level at a time; the next level's clause is fetched (L2) while
+        // this one is evaluated --------------------------------------------------------------------
+        bool any_choice = false;
+        RootClause nxt = {};
+        {
+            const int k = LS[0] + lane;
+            if (k < LS[1]) nxt = sched[k];
+        }
+        for (int L = 0; L < n_levels; ++L) {
+            const int k0 = LS[L], k_end = LS[L + 1];
+            RootClause rc = nxt;
+            if (L + 1 < n_levels) {
+                const int k = k_end + lane;
+                if (k < LS[L + 2]) nxt = sched[k];
+            }
+            for (int k = k0 + lane; k < k_end; k += 32) {
+                if (k >= k0 + 32) rc = sched[k];
+                const uint32_t op = rc.op_idx & 0xff;
+                const uint32_t idx = rc.op_idx >> 12;
+                int c = 0;
+                const ival o = eval_plan_clause(op, V[rc.lsrc], V[rc.rsrc], rc.imm, c);
+                V[3 + idx] = o;
+                LV[3 + idx] = uint8_t(L);
+                if (op >= OP_MIN_LI && op <= OP_MAX_LR) {
+                    any_choice |= (c != 0);
+                    C[idx] = uint8_t(c);
+                }
+            }
+            __syncwarp();
+        }
+        any_choice = __any_sync(kFull, any_choice);
+        const ival result = V[result_v];
+
+        // ---- classify (context.cu:289-321) ---------------------------------------------------
+        int out_position = -1;
+        bool pushing = false;
+        {
+            int verdict = 0;                                             // lane 0's view of the racy image wins
+            if (lane == 0) {
+                if (result.x > 0.0f) {
+                    // empty
+                } else if (DIM == 3 && __ldcg(&a.image[img_index]) > sz) {
+                    // hidden
+                } else if (result.y < 0.0f) {
+                    if (DIM == 3) atomicMax(&a.image[img_index], sz);
+                    else a.image[img_index] = 1;
+                } else {
+                    verdict = any_choice ? 2 : 1;
+                }
+            }
+            verdict = __shfl_sync(kFull, verdict, 0);
+            if (verdict) out_position = position;
+            pushing = verdict == 2;
+        }
+        int out_tape = parent.tape;
+        st_tiles += 1;
+        st_cells += unsigned(p_logical - 2 + 2 * ((p_logical <= kChunk ? 1 : 1 + (p_logical - 63 + 61) / 62) - 1));
+
+        if (pushing) {
+            // ---- mark: result -> operands, top level first ------------------------------------
+            if (lane == 0) A[result_v] = 1;
+            __syncwarp();
+            // A copy the parent's verdict left behind also keeps its unused operand's slot alive, i.e. the
+            // clause that wrote that slot last in the shortened tape (the plan's extra source, see
+            // k_eval_root).  Such an edge can point to a HIGHER dependency level than the copy sits on, which
+            // one top-down sweep has already passed: the sweep restarts from the highest level so marked
+            // until there is none (marks only grow, so the result is the backward walk's).
+            for (int top = n_levels - 1; top >= 0;) {
+                int late = -1;                                           // highest level marked behind the sweep's back
+                RootClause ahead = {};
+                {
+                    const int k = LS[top] + lane;
+                    if (k < LS[top + 1]) ahead = sched[k];
+                }
+                for (int L = top; L >= 0; --L) {
+                    const int k0 = LS[L], k_end = LS[L + 1];
+                    RootClause rc = ahead;
+                    if (L > 0) {
+                        const int k = LS[L - 1] + lane;
+                        if (k < k0) ahead = sched[k];
+                    }
+                    for (int k = k0 + lane; k < k_end; k += 32) {
+                        if (k >= k0 + 32) rc = sched[k];
+                        const uint32_t op = rc.op_idx & 0xff;
+                        const uint32_t idx = rc.op_idx >> 12;
+                        if (!A[3 + idx]) continue;
+                        const uint32_t lsrc = rc.lsrc, rsrc = rc.rsrc;
+                        const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[idx] : 0;
+                        const uint32_t extra = op == OP_COPY_LHS ? rsrc : (op == OP_COPY_IMM ? lsrc : 0u);
+                        if (extra > 3u && !A[extra] && int(LV[extra]) >= L) late = max(late, int(LV[extra]));
+                        if (c == 0) { A[lsrc] = 1; A[rsrc] = 1; }
+                        else if (c == 1) { A[lsrc] = 1; }
+                        else { A[rsrc] = 1; }
+                    }
+                    __syncwarp();
+                }
+                #pragma unroll
+                for (int o = 16; o; o >>= 1) late = max(late, __shfl_xor_sync(kFull, late, o));
+                top = late;
+            }
+            // ---- sweep: compact kept clauses in tape order (the parent's cells, as stored) ------
+            const uint64_t* const cells = arena + ptape;
+            const int per = (n + 31) / 32;
+            const int i_begin = 1 + lane * per, i_end = min(n + 1, i_begin + per);
+            int kept = 0;
+            for (int i = i_begin; i < i_end; ++i) {
+                if (!A[3 + i]) continue;
+                const uint32_t w = uint32_t(cells[chunked_index(i, p_logical)]);
+                const uint32_t op = w & 0xff, i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
+                const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[i] : 0;
+                const bool dropped = (c == 1 && i_lhs == i_out) || (c == 2 && i_rhs != 0 && i_rhs == i_out);
+                kept += dropped ? 0 : 1;
+            }
+            int incl = kept;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int offset = incl - kept;
+            const int total = __shfl_sync(kFull, incl, 31);
+            const int n_logical = total + 2;
+            const int n_chunks = n_logical <= kChunk ? 1 : 1 + (n_logical - 63 + 61) / 62;
+            int base = -1;
+            if (lane == 0) {
+                const int need = n_chunks * kChunk;
+                if (*(volatile int32_t*)a.tape_index < a.arena_cap) {
+                    base = atomicAdd(a.tape_index, need);
+                    if (base + need >= a.arena_cap) base = -1;         // arena exhausted: keep the parent tape
+                }
+            }
+            base = __shfl_sync(kFull, base, 0);
+            if (base >= 0) {
+                int q = 1 + offset;
+                for (int i = i_begin; i < i_end; ++i) {
+                    if (!A[3 + i]) continue;
+                    uint64_t d = cells[chunked_index(i, p_logical)];
+                    const uint32_t w = uint32_t(d);
+                    const uint32_t op = w & 0xff, i_out = (w >> 8) & 0xff, i_lhs = (w >> 16) & 0xff, i_rhs = w >> 24;
+                    const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[i] : 0;
+                    if (c == 1) {
+                        if (i_lhs == i_out) continue;
+                        d = (d & ~0xffull) | OP_COPY_LHS;
+                    } else if (c == 2) {
+                        if (i_rhs != 0 && i_rhs == i_out) continue;
+                        d = (d & ~0xffull) | (i_rhs ? OP_COPY_RHS : OP_COPY_IMM);
+                    }
+                    arena[base + chunked_index(q, n_logical)] = d;
+                    ++q;
+                }
+                if (lane == 0) {
+                    arena[base] = cells[0];                                                       // header
+                    arena[base + chunked_index(total + 1, n_logical)] = cells[chunked_index(n + 1, p_logical)];   // end cell
+                }
+                for (int c = lane; c < n_chunks; c += 32) {
+                    if (c > 0) arena[base + c * kChunk] = make_jump(-1);
+                    if (c + 1 < n_chunks) arena[base + c * kChunk + kChunk - 1] = make_jump(1);
+                }
+                out_tape = base;
+                st_ptiles += 1;
+                st_pcells += unsigned(n);
+                st_kept += unsigned(total + 2 + 2 * (n_chunks - 1));
+            }
+        }
+        if (lane == 0) {
+            a.tiles[tile_index].position = out_position;
+            a.tiles[tile_index].tape = out_tape;
+            a.tiles[tile_index].next = -1;
+        }
+    }
+    if (lane == 0 && st_tiles) {
+        atomicAdd(&a.ctl->stats[ST_I_TILES + a.level], st_tiles);
+        atomicAdd(&a.ctl->stats[ST_I_CELLS + a.level], st_cells);
+        atomicAdd(&a.ctl->stats[ST_I_SUB], st_tiles);
+        if (st_ptiles) {
+            atomicAdd(&a.ctl->stats[ST_P_TILES + a.level], st_ptiles);
+            atomicAdd(&a.ctl->stats[ST_P_CELLS + a.level], st_pcells);
+            atomicAdd(&a.ctl->stats[ST_P_KEPT + a.level], st_kept);
+            atomicAdd(&a.ctl->stats[ST_P_WRITTEN], st_kept);
+        }
     }
 }
 
@@ -1607,7 +2074,8 @@ k_normals(const NormalsArgs a, const Mat4 mat)
             // The walk is a chain of dependent loads (clause -> operands -> next clause) with few
             // warps to hide it, so the NEXT clause is fetched while this one runs; only a JUMP
             // (one per 62 cells) invalidates the prefetch.  The arena has a chunk of slack behind
-            // it, so reading one cell past an END cell is in bounds.
+            // it, so reading one cell past an END cell is in bounds.  (Four cells in flight instead of
+            // one changed nothing: the walk is bound by the lanes' opcode paths taking turns.)
             uint64_t ahead = __ldg(&arena[pos + 1]);
             while (__any_sync(kFull, active)) {
                 if (active) {
@@ -1845,6 +2313,8 @@ void init_kernels(int max_smem_optin) {
     opt_in(k_eval_tiles<3, false, true>, max_smem_optin);
     opt_in(k_eval_root<2>, max_smem_optin);
     opt_in(k_eval_root<3>, max_smem_optin);
+    opt_in(k_eval_sub<2>, max_smem_optin);
+    opt_in(k_eval_sub<3>, max_smem_optin);
     opt_in(k_eval_tiles<2, true, false, true>, max_smem_optin);
     opt_in(k_eval_tiles<2, false, false, true>, max_smem_optin);
     opt_in(k_eval_tiles<3, true, false, true>, max_smem_optin);
@@ -1898,6 +2368,17 @@ void launch_eval_root(int dim, const EvalRootArgs& a, const void* mat, cudaStrea
     const size_t smem = size_t(tiles_per_cta) * a.smem_per_tile;
     if (dim == 3) k_eval_root<3><<<grid, kRootThreads, smem, s>>>(a, *static_cast<const Mat4*>(mat));
     else k_eval_root<2><<<grid, kRootThreads, smem, s>>>(a, *static_cast<const Mat3*>(mat));
+}
+
+int sub_warps(int slice) {
+    return std::max(1, std::min(kSubMaxWarps, (110 * 1024) / std::max(slice, 1)));
+}
+
+void launch_eval_sub(int dim, const EvalSubArgs& a, const void* mat, int grid, cudaStream_t s) {
+    const int warps = sub_warps(a.slice);
+    const size_t smem = size_t(warps) * a.slice;
+    if (dim == 3) k_eval_sub<3><<<grid, warps * 32, smem, s>>>(a, *static_cast<const Mat4*>(mat));
+    else k_eval_sub<2><<<grid, warps * 32, smem, s>>>(a, *static_cast<const Mat3*>(mat));
 }
 
 void launch_rank_tiles(int dim, const RankArgs& a, int grid, cudaStream_t s) {

@@ -43,11 +43,16 @@ struct EvalTilesArgs {
     unsigned long long* heat; // S x S accumulators, units of 1/4096 cell
     int32_t heat_px;          // this level's tile edge in pixels
     int32_t n_root;           // clauses of the root tape (its walk is charged without the layout's JUMPs)
+    // Small levels (k_eval_sub): parents that carry a clause-parallel plan are left to that kernel
+    // when the level has at most sub_max_parents parents.  Null / 0 otherwise.
+    const int32_t* plan_of;
+    int32_t sub_max_parents;
 };
 
 // One clause of a root tape in SSA / dependency-level order (built on the host per Tape).
 struct RootClause {
-    uint32_t op_idx;   // bits 0-7 opcode, bit 8 "verdict past the 4096-entry record", bits 12+ clause index
+    uint32_t op_idx;   // bits 0-7 opcode, bit 8 "verdict past the 4096-entry record", bits 9 / 10 "left / right operand
+                       // sits in the output slot" (root plans), bits 12+ clause index
     uint32_t lsrc;     // value id of the left operand  (0 none, 1..3 x/y/z, 3+i = clause i)
     uint32_t rsrc;     // value id of the right operand
     float imm;
@@ -77,6 +82,53 @@ struct EvalRootArgs {
     int32_t result_v;         // value id of the tape's result
     int32_t group;            // threads per tile: 32, 64, 128 or 256
     int32_t smem_per_tile;    // bytes: values + verdicts + liveness + scratch
+    float z;
+    // Clause-parallel plans of the shortened tapes (see k_eval_sub); plans == null: none are written.
+    int32_t* plans;           // plan arena (32-bit words)
+    int32_t* plan_cursor;     // allocation cursor in words (FrameCtl::plan_cursor)
+    int32_t plan_cap;         // arena size in words
+    int32_t* plan_of;         // per level-0 tile: word offset of its plan, -1 = none
+    int32_t sub_slice;        // shared memory k_eval_sub has per tile: larger plans are not written
+    int32_t* plan_count;      // FrameCtl::plan_count
+    int32_t max_plans;        // no more plans than a small level has parents
+    int32_t plan_min;         // shortened tapes with fewer clauses get no plan (kPlanMinClauses; tests lower it)
+    const uint16_t* prevw;    // per clause i: value id that lived in its output slot before it (0 = none)
+};
+
+// A shortened tape's plan in the plan arena: kPlanHeader words, then n_levels + 1 level offsets, then
+// the clauses (RootClause, 4 words each) in dependency-level order.
+enum { PL_N = 0,          // clauses of the shortened tape (logical cells 1 .. n)
+       PL_LEVELS = 1,     // dependency levels (those of the root tape; some may be empty)
+       PL_RESULT = 2,     // value id of the result
+       PL_TAPE = 3,       // arena index of the tape itself (contiguous chunked run)
+       PL_LOGICAL = 4,    // its logical cell count, n + 2
+       PL_VALUES = 5,     // value ids in use: 4 + n + forwarding nodes
+       PL_SCHED = 6,      // word offset of the clause array from the plan's first word
+       PL_COUNT = 7 };    // entries in the clause array (n + forwarding nodes)
+constexpr int kPlanHeader = 8;
+constexpr int kPlanMaxClauses = 4000;   // < kMaxChoices: every verdict of a planned tape is recorded
+constexpr int kPlanMinClauses = 160;    // shorter tapes are walked serially faster than their levels can be swept
+constexpr int kSubMaxWarps = 16;
+
+struct EvalSubArgs {
+    uint64_t* arena;
+    int32_t* tape_index;
+    int32_t arena_cap;
+    int32_t* image;           // this level's filled image
+    TileNode* tiles;          // this level's tile records (written)
+    int32_t tiles_cap;
+    uint32_t tps;
+    const TileNode* ptiles;   // parent level
+    const int32_t* pactive;
+    const int32_t* n_parents;
+    uint32_t ptps;
+    FrameCtl* ctl;
+    int32_t* queue;
+    int32_t level;
+    const int32_t* plans;
+    const int32_t* plan_of;   // indexed like ptiles
+    int32_t slice;            // shared-memory bytes per warp (= per tile)
+    int32_t max_parents;      // the kernel stands down when the level has more parents than this
     float z;
 };
 
@@ -143,6 +195,11 @@ void launch_heat_finish(const unsigned long long* units, float* heat, long long 
 void launch_begin_frame(FrameCtl* ctl, int32_t first_free, cudaStream_t s);
 void launch_eval_tiles(int dim, bool root, const EvalTilesArgs& a, const void* mat, int grid, cudaStream_t s);
 void launch_eval_root(int dim, const EvalRootArgs& a, const void* mat, cudaStream_t s);
+// Shared memory a tile of k_eval_sub needs for a plan with nv value ids and n_levels levels.
+__host__ __device__ inline int sub_need_bytes(int nv, int n_levels) { return ((nv * 11 + 3) & ~3) + 4 * (n_levels + 1); }
+// Warps per CTA of k_eval_sub for a per-tile slice (two CTAs share an SM).
+int sub_warps(int slice);
+void launch_eval_sub(int dim, const EvalSubArgs& a, const void* mat, int grid, cudaStream_t s);
 void launch_rank_tiles(int dim, const RankArgs& a, int grid, cudaStream_t s);
 void launch_upsample_filled(int dim, const int32_t* prev, int32_t* image, int size, int grid, cudaStream_t s);
 void launch_eval_pixels(const EvalVoxelsArgs& a, const Mat3& mat, int grid, cudaStream_t s);

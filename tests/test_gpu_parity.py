@@ -215,6 +215,29 @@ def test_exchange_kernels_reassemble_the_frame(model, dim, size, world, col_step
     full.close()
 
 
+@pytest.mark.parametrize("model,dim,size,world", [("prospero", 2, 1024, 4), ("bear", 3, 512, 8), ("hello_world", 3, 256, 1)])
+def test_publish_fills_one_host_frame_from_every_shard(model, dim, size, world):
+    """mprb_ctx_publish: each sharded context stores the blocks it owns straight into ONE full-size frame in
+    page-locked host memory (no device-side gather); together they make the single-context frame."""
+    import torch
+    full, tape = render(model, dim, size)
+    img = torch.zeros((size, size), dtype=torch.int32).pin_memory()
+    nrm = torch.zeros((size, size), dtype=torch.int32).pin_memory() if dim == 3 else None
+    for r in range(world):
+        opts = sharding.diagonal_tiles(size, world, r) if world > 1 else {}
+        part = capi.Context(size, num_subtapes=SUBTAPES, **opts)
+        (part.render2D if dim == 2 else part.render3D)(tape)
+        part.publish(dim, img.data_ptr(), nrm.data_ptr() if dim == 3 else 0)
+        part.close()
+    assert np.array_equal(img.numpy(), full.image())
+    if dim == 3:
+        assert np.array_equal(nrm.numpy().view(np.uint32), full.normals())
+    pageable = np.zeros((size, size), dtype=np.int32)
+    with pytest.raises(capi.MprbError):
+        full.publish(dim, pageable.ctypes.data)
+    full.close()
+
+
 def test_arena_exhaustion_degrades_like_the_reference():
     """With a tiny arena, tiles keep their parent tape (reference context.cu:336-347); the image
     is still correct because every tape that was kept is valid for its tile."""
@@ -282,7 +305,8 @@ def test_float_pass_work_items_of_several_tiles_give_the_reference_frame(name, g
     import sys
     model, dim, size = name.rsplit("_", 2)
     want = json.loads((ROOT / "tests" / "golden" / "ref" / f"{name}.json").read_text())
-    env = dict(os.environ, MPRB_FLOAT_GROUP=str(group))
+    # MPRB_SUB_WAVES=0: tiles of small levels evaluated by k_eval_sub get a tape each (nothing to share)
+    env = dict(os.environ, MPRB_FLOAT_GROUP=str(group), MPRB_SUB_WAVES="0")
     r = subprocess.run([sys.executable, str(ROOT / "tools" / "frame_digest.py"), model, dim[0], size],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -292,6 +316,35 @@ def test_float_pass_work_items_of_several_tiles_give_the_reference_frame(name, g
         assert got["normals"] == want["normals"]["sha"]
     assert 0 < got["f_items"] < got["f_tiles"]
     assert 0 < got["p_written"] < got["p_kept"]
+
+
+@pytest.mark.parametrize("waves", [0, 4, 100000])
+@pytest.mark.parametrize("name", ["prospero_2d_256", "prospero_2d_512", "prospero_2d_1024", "bear_3d_256", "bear_3d_512",
+                                  "hello_world_2d_256", "hello_world_3d_128", "architecture_3d_256",
+                                  "involute_gear_2d_2d_512", "involute_gear_3d_3d_256"])
+def test_small_levels_evaluated_clause_parallel_give_the_reference_frame(name, waves, monkeypatch):
+    """Levels with few tiles are evaluated one warp per tile on the dependency-level plan k_eval_root
+    writes with each shortened tape (k_eval_sub) instead of one lane per tile walking the tape clause
+    by clause.  MPRB_SUB_WAVES (read when a context is made) = how many waves of tiles still count as
+    few: 0 switches the kernel off, a huge value sends every planned tile through it.  Images, tile
+    records and every tile's shortened tape are the reference build's either way."""
+    case = [c for c in CASES if c[0] == name][0]
+    _, model, dim, size, summary, npz = case
+    monkeypatch.setenv("MPRB_SUB_WAVES", str(waves))
+    ctx, tape = render(model, dim, size)
+    fp = parity.fingerprint(ctx, dim)
+    bad = parity.compare_summary(summary, parity.summarize(fp))
+    assert not bad, bad
+    if npz is not None:
+        ref = dict(np.load(npz))
+        ref["dim"], ref["size"] = dim, size
+        assert not parity.compare(ref, fp)
+    st = ctx.stats()
+    if waves == 0:
+        assert st.i_sub_tiles == 0
+    elif waves == 100000 and model != "hello_world":
+        assert 0 < st.i_sub_tiles <= st.i_tiles[1]
+    ctx.close()
 
 
 @pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built")

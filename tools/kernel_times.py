@@ -44,13 +44,13 @@ def main():
             st = ctx.stats()
             gpu.append(st.gpu_ms)
             ks.append(list(st.kernel_ms)[: st.n_launches])
-        k = np.mean(np.array(ks), axis=0)
+        k = np.median(np.array(ks), axis=0)
         names = NAMES3 if dim == 3 else NAMES2
-        row = {"gpu_ms": float(np.mean(gpu)), "gpu_ms_min": float(np.min(gpu)),
+        row = {"gpu_ms": float(np.median(gpu)), "gpu_ms_min": float(np.min(gpu)),
                "kernels": {n: round(float(v), 4) for n, v in zip(names, k)},
                "float_tiles": int(st.f_tiles), "float_cells": int(st.f_cells), "float_items": int(st.f_items),
                "push_tiles": list(st.p_tiles), "push_kept": list(st.p_kept), "push_written": int(st.p_written),
-               "n_active": list(st.n_active), "interval_tiles": list(st.i_tiles), "interval_cells": list(st.i_cells)}
+               "n_active": list(st.n_active), "i_sub_tiles": int(st.i_sub_tiles), "interval_tiles": list(st.i_tiles), "interval_cells": list(st.i_cells)}
         out[case] = row
         print(case, json.dumps(row), flush=True)
         ctx.close()
