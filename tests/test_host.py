@@ -552,3 +552,21 @@ def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation(G, 
                 got += [b2f(m.tmem[TB + 2 * s]), b2f(m.tmem[TB + 2 * s + 1])]
             got = np.array(got, dtype=f32)
             assert ((got == v) | (np.isnan(got) & np.isnan(v))).all(), (trial, s, got, v)
+
+
+@pytest.mark.parametrize("model", ["prospero", "architecture", "bear", "involute_gear_2d", "hello_world"])
+def test_planned_marking_keeps_the_clauses_the_reference_slot_walk_keeps(model):
+    """k_eval_sub marks a dependency-level plan instead of walking the parent's shortened tape backwards
+    slot by slot (tests/plan_model.py models both).  On arbitrary verdicts the clauses a child keeps must
+    be the same - including those the reference keeps only because a copy left behind by a verdict still
+    names its unused operand's slot, and including marks that land on a level the top-down sweep has
+    already passed (at least one of these cases needs the second sweep)."""
+    import plan_model
+    cells = load_tape(model)
+    most_sweeps = 0
+    for seed, (p_root, p_child) in enumerate([(0.2, 0.1), (0.1, 0.3), (0.5, 0.05), (0.05, 0.05), (0.3, 0.6)]):
+        ref, mine, sweeps = plan_model.compare(cells, seed, p_root, p_child)
+        assert ref == mine, (model, seed, len(ref), len(mine))
+        most_sweeps = max(most_sweeps, sweeps)
+    if model == "prospero":
+        assert most_sweeps >= 2
