@@ -244,8 +244,8 @@ def run_mine(args, workloads):
         # pointed at a per-rank log for the whole run and the one JSON line goes to the real stdout
         # (OUT) at the end; rank 0 copies the log to stderr and the communicator lines into the JSON line
         # ("nccl") once the group is up.
-        os.environ.setdefault("NCCL_DEBUG", os.environ.get("MPRB_NCCL_DEBUG", "INFO"))
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ["NCCL_DEBUG"] = os.environ.get("MPRB_NCCL_DEBUG", "INFO")    # whatever the box's default is
+        os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("MPRB_NCCL_DEBUG_SUBSYS", "INIT")
         os.environ.pop("NCCL_DEBUG_FILE", None)
         divert_stdout(f"/tmp/mprb_stdout_{os.getpid()}_rank{rank}.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -668,6 +668,16 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # NCCL takes its debug level from the environment it was loaded under: with several ranks, make sure
+    # NCCL_DEBUG=INFO (communicator lines: rank / nranks) is in place before anything imports torch, by
+    # replacing this process with itself once (same PID, so the launcher does not notice).
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not os.environ.get("MPRB_BENCH_REEXEC"):
+        os.environ["MPRB_BENCH_REEXEC"] = "1"
+        os.environ["NCCL_DEBUG"] = os.environ.get("MPRB_NCCL_DEBUG", "INFO")
+        os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("MPRB_NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.pop("NCCL_DEBUG_FILE", None)
+        sys.stdout.flush()
+        os.execv(sys.executable, [sys.executable] + sys.argv)
     workloads = parse_workloads(args.workload)
     if args.impl == "reference":
         run_reference(args, workloads)

@@ -136,7 +136,8 @@ struct mprb_ctx {
     long long plans_words = 0;
     int32_t* plan_of = nullptr;      // device: per level-0 tile, word offset of its plan or -1
     long long plan_of_cap = 0;
-    int sub_waves = 4;               // k_eval_sub serves levels of up to this many waves of tiles; MPRB_SUB_WAVES (0 = off)
+    int sub_waves = -1;              // k_eval_sub serves levels of up to this many waves of tiles; -1 = from the tape's
+                                     // shape (see render), MPRB_SUB_WAVES overrides (0 = off)
     // What the last frame of (hint_tape, hint_dim) looked like: plans cost k_eval_root time and k_eval_sub a
     // launch, so both are skipped while the level below the root is large or its tapes are too short to
     // plan (looked at again every 32nd frame; the frame itself is the same either way).
@@ -442,14 +443,25 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
     int sub_slice = 0, sub_max_parents = 0, sub_grid = 0;
     const bool hinted = c->hint_tape == static_cast<const void*>(plan) && c->hint_dim == dim && c->sub_waves < 100000 &&
                         (c->frame_no++ & 31u) != 31u;
-    if (clause_parallel_root && c->sub_waves > 0 && n_levels >= 2 && td->prevw && plan->n_levels < 256) {
+    // How many waves of k_eval_sub still beat one lane per tile walking the tape: a tile there costs about its
+    // levels (~1000 cycles each: fetch, divergent interval operators, two sweeps) plus ~30 cycles per clause,
+    // against two walks of the tape at ~400 (renamed slots: ~800) cycles a clause here; half the root tape's
+    // length stands in for the shortened tapes'.  bear (72 levels x 7.6 clauses): 1 wave; prospero (22 x 275): 8.
+    int sub_waves = c->sub_waves;
+    if (sub_waves < 0) {
+        const double half = 0.5 * (n_cells - 2);
+        const double serial = half * (use_remap(n_slots) ? 800.0 : 400.0);
+        const double parallel = 1000.0 * plan->n_levels + 30.0 * half;
+        sub_waves = std::max(1, std::min(8, int(serial / parallel)));
+    }
+    if (clause_parallel_root && sub_waves > 0 && n_levels >= 2 && td->prevw && plan->n_levels < 256) {
         const int need = sub_need_bytes(n_cells - 2 + 4, plan->n_levels);
         sub_slice = std::min(std::max((need + 15) / 16 * 16, 2048), 24576);
         const int warps = sub_warps(sub_slice);
         const int ctas = (2 * (warps * sub_slice + 1024) <= 227 * 1024) ? 2 : 1;
         sub_grid = c->sm_count * ctas;
-        sub_max_parents = std::max(1, c->sub_waves * sub_grid * warps / 64);
-        if (hinted && (c->hint_parents > 2 * sub_max_parents || c->hint_plans == 0)) sub_slice = 0;
+        sub_max_parents = std::max(1, sub_waves * sub_grid * warps / 64);
+        if (hinted && (c->hint_parents > sub_max_parents + sub_max_parents / 8 || c->hint_plans == 0)) sub_slice = 0;
     }
     if (sub_slice) {
         const long long per_plan = kPlanHeader + plan->n_levels + 4 + 4LL * (sub_slice / 10 + 1);

@@ -199,6 +199,7 @@ void launch_eval_root(int dim, const EvalRootArgs& a, const void* mat, cudaStrea
 __host__ __device__ inline int sub_need_bytes(int nv, int n_levels) { return ((nv * 11 + 3) & ~3) + 4 * (n_levels + 1); }
 // Warps per CTA of k_eval_sub for a per-tile slice (two CTAs share an SM).
 int sub_warps(int slice);
+bool use_remap(int n_slots);      // tapes with too many slots for shared-memory rows go through slot renaming
 void launch_eval_sub(int dim, const EvalSubArgs& a, const void* mat, int grid, cudaStream_t s);
 void launch_rank_tiles(int dim, const RankArgs& a, int grid, cudaStream_t s);
 void launch_upsample_filled(int dim, const int32_t* prev, int32_t* image, int size, int grid, cudaStream_t s);

@@ -1,0 +1,6 @@
+set -x
+for L in build/old/libmprb.so mpr_b200/libmprb.so; do
+echo "== LIB $L"
+MPRB_LIBRARY=$PWD/$L python tools/kernel_times.py bear:3:1024 hello_world:3:1024 bear:3:512 architecture:3:1024 involute_gear_3d:3:1024 2>&1 | cut -c1-420
+done
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "fixture or work_items" 2>&1 | tail -2
