@@ -345,7 +345,7 @@ int cached_occupancy(mprb_ctx* c, int kind, int dim, bool root, int n_slots, int
     if (itr != c->occ_cache.end()) return itr->second;
     int n = 0;
     if (kind == 0) n = occupancy_eval_tiles(dim, root, n_slots);
-    else if (kind == 1) n = float_ctas(dim, n_slots, group, float_tmem(n_slots, false) && group == 2);
+    else if (kind == 1) n = float_ctas(dim, n_slots, group, float_tmem(n_slots, false) && group >= 2);
     else n = occupancy_normals(n_slots);
     n = std::max(n, 1);
     c->occ_cache[key] = n;
@@ -464,7 +464,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         if (hinted && (c->hint_parents > sub_max_parents + sub_max_parents / 8 || c->hint_plans == 0)) sub_slice = 0;
     }
     if (sub_slice) {
-        const long long per_plan = kPlanHeader + plan->n_levels + 4 + 4LL * (sub_slice / 10 + 1);
+        const long long per_plan = kPlanHeader + plan->n_levels + 4 + 5LL * (sub_slice / 10 + 1);
         // never more plans than root tiles; the arena running out only sends tiles to the serial kernel
         const long long want = std::min<long long>(per_plan * (std::min<long long>(sub_max_parents, count0) + 8), 64LL << 20);
         if (c->plans_words < want) {

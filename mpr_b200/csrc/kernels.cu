@@ -966,7 +966,7 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
         // A plan for k_eval_sub goes with the tape when it is small enough for that kernel's per-tile
         // shared memory and the level can still turn out small (max_plans parents at most).
         const int plan_nv = 4 + total;
-        const int plan_words = kPlanHeader + ((a.n_levels + 1 + 3) & ~3) + 4 * total;
+        const int plan_words = kPlanHeader + ((a.n_levels + 1 + 3) & ~3) + 5 * total;      // clauses + (at most) as many extra edges
         const bool plan_fits = a.plans != nullptr && total <= kPlanMaxClauses && total >= a.plan_min && nv >= 4 * G + 8 &&
                                sub_need_bytes(plan_nv, a.n_levels) <= a.sub_slice;
         if (t == 0) {
@@ -990,8 +990,8 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
         const int pb = scratch[13];
         // N[v] = value id in the shortened tape's plan (3 + its cell number), kNotInTape for a live clause
         // that was dropped; the values themselves are done with, N takes their place.
-        uint32_t* const N = reinterpret_cast<uint32_t*>(mine);
-        constexpr uint32_t kNotInTape = 0xffffffffu;
+        uint16_t* const N = reinterpret_cast<uint16_t*>(mine);      // 3 + total <= kPlanMaxClauses + 3 where it is used
+        constexpr uint32_t kNotInTape = 0xffffu;
         if (base >= 0) {
             int q = 1 + offset;
             for (int i = i_begin; i < i_end; ++i) {
@@ -1009,11 +1009,11 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
                     d = (d & ~0xffull) | (i_rhs ? OP_COPY_RHS : OP_COPY_IMM);
                 }
                 if (dropped) {
-                    if (pb >= 0) N[3 + i] = kNotInTape;
+                    if (pb >= 0) N[3 + i] = uint16_t(kNotInTape);
                     continue;
                 }
                 arena[base + chunked_index(q, n_logical)] = d;
-                if (pb >= 0) N[3 + i] = uint32_t(3 + q);
+                if (pb >= 0) N[3 + i] = uint16_t(3 + q);
                 ++q;
             }
             if (t == 0) {
@@ -1042,30 +1042,34 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
             // alive whatever kept clause wrote the slot last.  Both cases are one question: which clause of
             // the shortened tape wrote this slot last?  P[i] = the value that sat in clause i's output slot
             // before it (host-built, api.cu); following it from the operand's root producer answers it.
-            uint16_t* const P = reinterpret_cast<uint16_t*>(mine + size_t(nv) * 4);
+            uint16_t* P = reinterpret_cast<uint16_t*>(mine + size_t(nv) * 2);          // behind N
+            uint16_t* P2 = reinterpret_cast<uint16_t*>(mine + size_t(nv) * 4);         // the other copy (see below)
             for (int i = t; i <= n; i += G) P[i] = a.prevw[i];
-            if (t < 4) N[t] = uint32_t(t);                                // none, x, y, z
+            if (t < 4) N[t] = uint16_t(t);                                // none, x, y, z
             group_sync(bar, G);                                           // N, P complete
             auto in_tape = [&](uint32_t p) { return A[p] && N[p] != kNotInTape; };
             // Slots are reused hundreds of times and most of their writers are dead in any one tile:
             // pointer jumping first (P[i] skips writers that left the tape; log2(chain) rounds), so that a
-            // lookup is a hop or two.  In-place is safe: P[i] only ever moves to an earlier writer of the same
-            // slot with nothing kept in between, whichever of a neighbour's old / new value it reads.
+            // lookup is a hop or two.  Each round reads one copy and writes the other.
             for (;;) {
                 if (t == 0) scratch[14] = 0;
                 group_sync(bar, G);
                 bool moved = false;
                 for (int i = 1 + t; i <= n; i += G) {
-                    const uint32_t p = P[i];
+                    uint32_t p = P[i];
                     if (p > 3u && !in_tape(p)) {
-                        P[i] = P[p - 3u];
+                        p = P[p - 3u];
                         moved = true;
                     }
+                    P2[i] = uint16_t(p);
                 }
                 if (moved) scratch[14] = 1;
                 group_sync(bar, G);
                 const bool again = scratch[14] != 0;
-                group_sync(bar, G);
+                group_sync(bar, G);                                       // everyone has read the flag before it is reset
+                uint16_t* const tmp = P;
+                P = P2;
+                P2 = tmp;
                 if (!again) break;
             }
             auto in_plan = [&](uint32_t p) -> uint32_t {                  // root value id -> plan value id
@@ -1091,6 +1095,9 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
             int32_t* const pls = hdr + kPlanHeader;
             const int sched_off = kPlanHeader + ((a.n_levels + 1 + 3) & ~3);
             RootClause* const out = reinterpret_cast<RootClause*>(hdr + sched_off);
+            uint32_t* const extras = reinterpret_cast<uint32_t*>(hdr + sched_off + 4 * total);
+            if (t == 0) scratch[15] = 0;                                  // how many (read again behind the next barrier)
+            group_sync(bar, G);
             for (int k = k_begin; k < k_end; ++k) {
                 if (!KS[k]) continue;
                 const RootClause rc = a.sched[k];
@@ -1114,8 +1121,11 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
                 }
                 e.op_idx |= (N[3 + idx] - 3u) << 12;
                 out[pp++] = e;
+                // the source a copy only keeps alive (k_eval_sub marks those in a pass of their own)
+                const uint32_t extra = c == 0 ? 0u : ((c == 1 || rc.rsrc != 0) ? e.rsrc : e.lsrc);
+                if (extra != 0) extras[atomicAdd(&scratch[15], 1)] = (N[3 + idx] - 3u) | (extra << 16);
             }
-            group_sync(bar, G);                                           // PP complete
+            group_sync(bar, G);                                           // PP, extras complete
             for (int L = t; L < a.n_levels; L += G) {                     // where each level starts in the plan
                 const int ks = a.level_start[L];
                 const int owner = ks / per;
@@ -1132,7 +1142,7 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
                 hdr[PL_LOGICAL] = n_logical;
                 hdr[PL_VALUES] = plan_nv;
                 hdr[PL_SCHED] = sched_off;
-                hdr[PL_COUNT] = total;
+                hdr[PL_EXTRAS] = scratch[15];
                 a.plan_of[tile] = pb;
             }
         }
@@ -1225,6 +1235,8 @@ k_eval_sub(const EvalSubArgs a, const typename MatOf<DIM>::type mat)
         const int n = hdr[PL_N], n_levels = hdr[PL_LEVELS], result_v = hdr[PL_RESULT];
         const int ptape = hdr[PL_TAPE], p_logical = hdr[PL_LOGICAL], nv = hdr[PL_VALUES];
         const RootClause* __restrict__ const sched = reinterpret_cast<const RootClause*>(hdr + hdr[PL_SCHED]);
+        const uint32_t* __restrict__ const extras = reinterpret_cast<const uint32_t*>(hdr + hdr[PL_SCHED] + 4 * n);
+        const int n_extras = hdr[PL_EXTRAS];
         float2* const V = reinterpret_cast<float2*>(mine);
         uint8_t* const C = mine + size_t(nv) * 8;
         uint8_t* const A = C + nv;
@@ -1281,7 +1293,10 @@ k_eval_sub(const EvalSubArgs a, const typename MatOf<DIM>::type mat)
                 const uint32_t op = rc.op_idx & 0xff;
                 const uint32_t idx = rc.op_idx >> 12;
                 int c = 0;
-                const ival o = eval_plan_clause(op, V[rc.lsrc], V[rc.rsrc], rc.imm, c);
+                // a copy's other source is only there for the mark phase (it may sit on this very level)
+                const ival Lv = op == OP_COPY_IMM ? iv(0.0f, 0.0f) : V[rc.lsrc];
+                const ival Rv = op == OP_COPY_LHS ? iv(0.0f, 0.0f) : V[rc.rsrc];
+                const ival o = eval_plan_clause(op, Lv, Rv, rc.imm, c);
                 V[3 + idx] = o;
                 LV[3 + idx] = uint8_t(L);
                 if (op >= OP_MIN_LI && op <= OP_MAX_LR) {
@@ -1328,8 +1343,11 @@ k_eval_sub(const EvalSubArgs a, const typename MatOf<DIM>::type mat)
             // k_eval_root).  Such an edge can point to a HIGHER dependency level than the copy sits on, which
             // one top-down sweep has already passed: the sweep restarts from the highest level so marked
             // until there is none (marks only grow, so the result is the backward walk's).
+            // So: a top-down sweep over the operands proper (they sit on lower levels: what a level reads
+            // and what it writes never meet), then one pass over all live copies that first LOOKS at their extra
+            // sources and then, behind a barrier, marks them; a mark that landed on a level the sweep had
+            // passed restarts the sweep from there.
             for (int top = n_levels - 1; top >= 0;) {
-                int late = -1;                                           // highest level marked behind the sweep's back
                 RootClause ahead = {};
                 {
                     const int k = LS[top] + lane;
@@ -1347,13 +1365,25 @@ k_eval_sub(const EvalSubArgs a, const typename MatOf<DIM>::type mat)
                         const uint32_t op = rc.op_idx & 0xff;
                         const uint32_t idx = rc.op_idx >> 12;
                         if (!A[3 + idx]) continue;
-                        const uint32_t lsrc = rc.lsrc, rsrc = rc.rsrc;
                         const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[idx] : 0;
-                        const uint32_t extra = op == OP_COPY_LHS ? rsrc : (op == OP_COPY_IMM ? lsrc : 0u);
-                        if (extra > 3u && !A[extra] && int(LV[extra]) >= L) late = max(late, int(LV[extra]));
-                        if (c == 0) { A[lsrc] = 1; A[rsrc] = 1; }
-                        else if (c == 1) { A[lsrc] = 1; }
-                        else { A[rsrc] = 1; }
+                        if (op == OP_COPY_IMM) continue;                          // its one source is an extra edge
+                        if (c != 2) A[rc.lsrc] = 1;
+                        if (c != 1 && op != OP_COPY_LHS) A[rc.rsrc] = 1;          // a copy's rsrc is an extra edge
+                    }
+                    __syncwarp();
+                }
+                int late = -1;                                                    // highest level an extra edge newly marks
+                for (int k0 = 0; k0 < n_extras; k0 += 32) {
+                    uint32_t extra = 0;
+                    if (k0 + lane < n_extras) {
+                        const uint32_t e = extras[k0 + lane];
+                        if (A[3 + (e & 0xffffu)]) extra = e >> 16;
+                    }
+                    const bool fresh = extra != 0 && !A[extra];
+                    __syncwarp();                                                 // all looked before anyone marks
+                    if (fresh) {
+                        A[extra] = 1;
+                        if (extra > 3u) late = max(late, int(LV[extra]));
                     }
                     __syncwarp();
                 }
@@ -1609,13 +1639,22 @@ __device__ __forceinline__ void run_float_clauses<4>(uint32_t& cp, uint32_t& w, 
 
 // G = 2 with tile 1's value rows in TENSOR MEMORY (tools/gen_float_loop.py, `tmem`): tb = address of this
 // warp's column group minus 2 (slot id s -> columns 2 (s - 1), 2 (s - 1) + 1).
+template <int G>
 __device__ __forceinline__ void run_float_clauses_tm(uint32_t& cp, uint32_t& w, uint32_t& imm, uint32_t sb, uint32_t tb)
 {
-    asm volatile(
+    if (G == 4) {          // tiles 0, 1 in shared memory, tiles 2, 3 in tensor memory (four columns per slot)
+        asm volatile(
+#include "float_loop_ptx_g4t.inc"
+            : "+r"(cp), "=&r"(w), "=&r"(imm)
+            : "r"(sb), "r"(tb)
+            : "memory");
+    } else {
+        asm volatile(
 #include "float_loop_ptx_g2t.inc"
-        : "+r"(cp), "=&r"(w), "=&r"(imm)
-        : "r"(sb), "r"(tb)
-        : "memory");
+            : "+r"(cp), "=&r"(w), "=&r"(imm)
+            : "r"(sb), "r"(tb)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void tm_st2(uint32_t taddr, float2 v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "f"(v.x), "f"(v.y) : "memory");
@@ -1686,9 +1725,10 @@ template <bool REMAP, int G, bool TM>
 __device__ __forceinline__ void walk_float(TapeStream<REMAP, REMAP>& ts, int tape, Slots2<REMAP>& slots, unsigned& cells,
                                            float2 (&r)[G], uint32_t tb)
 {
-    constexpr int SHIFT = TM ? 0 : (G == 4 ? 2 : (G == 2 ? 1 : 0));      // TM: shared-memory rows keep the G = 1 layout
+    constexpr int GS = TM ? G / 2 : G;                                   // tiles per shared-memory row (TM: the other half sits in tensor memory)
+    constexpr int SHIFT = GS == 4 ? 2 : (GS == 2 ? 1 : 0);
     static_assert(!REMAP || G == 1, "renamed slots: one tile per warp");
-    static_assert(!TM || G == 2, "tensor-memory rows: two tiles per warp");
+    static_assert(!TM || G == 2 || G == 4, "tensor-memory rows: half of two or four tiles per warp");
     if (ts.fetch(tape) && !REMAP) annotate_chunk<kFastOps, kUsesLhs, kUsesRhs, SHIFT>(ts.buf);
     uint32_t cp = ts.rd + ((tape & (kChunk - 1)) << 3);
     uint32_t seg = cp;
@@ -1700,7 +1740,7 @@ __device__ __forceinline__ void walk_float(TapeStream<REMAP, REMAP>& ts, int tap
             w = d.x;
             immb = d.y;
         } else if (TM) {
-            run_float_clauses_tm(cp, w, immb, slots.base, tb);
+            run_float_clauses_tm<G>(cp, w, immb, slots.base, tb);
         } else {
             run_float_clauses<G>(cp, w, immb, slots.base);
         }
@@ -1718,8 +1758,11 @@ __device__ __forceinline__ void walk_float(TapeStream<REMAP, REMAP>& ts, int tap
             const float2 L = slots.ld(off_lhs2(w));
             slots.st(off_out2(w), float_clause(op, L, slots.ld(off_rhs2(w)), __uint_as_float(immb)));
         } else if (TM) {
-            sts_f2(slots.base + off_out2(w), float_clause_libdevice(op, lds_f2(slots.base + off_lhs2(w))));
-            tm_st2(tb + tm_col(off_out2(w)), float_clause_libdevice(op, tm_ld2(tb + tm_col(off_lhs2(w)))));
+            #pragma unroll
+            for (int g = 0; g < GS; ++g) {
+                sts_f2(slots.base + off_out2(w) + 8 * g, float_clause_libdevice(op, lds_f2(slots.base + off_lhs2(w) + 8 * g)));
+                tm_st2(tb + tm_col(off_out2(w)) + 2 * g, float_clause_libdevice(op, tm_ld2(tb + tm_col(off_lhs2(w)) + 2 * g)));
+            }
         } else {
             #pragma unroll
             for (int g = 0; g < G; ++g) {
@@ -1731,8 +1774,11 @@ __device__ __forceinline__ void walk_float(TapeStream<REMAP, REMAP>& ts, int tap
     if (REMAP) {
         r[0] = slots.ld(off_out2(w));
     } else if (TM) {
-        r[0] = lds_f2(slots.base + off_out2(w));
-        r[1 % G] = tm_ld2(tb + tm_col(off_out2(w)));
+        #pragma unroll
+        for (int g = 0; g < GS; ++g) {
+            r[g] = lds_f2(slots.base + off_out2(w) + 8 * g);
+            r[(GS + g) % G] = tm_ld2(tb + tm_col(off_out2(w)) + 2 * g);
+        }
     } else {
         #pragma unroll
         for (int g = 0; g < G; ++g) r[g] = lds_f2(slots.base + off_out2(w) + 8 * g);
@@ -1759,7 +1805,7 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
     Stream ts;
     ts.init(s_dyn + warp * Stream::stride(), a.arena, a.arena_cap);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
-    constexpr int GS = TM ? 1 : G;     // tiles whose rows live in shared memory
+    constexpr int GS = TM ? G / 2 : G; // tiles whose rows live in shared memory (TM: the other half in tensor memory)
     Slots2<REMAP> slots;
     slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * GS) * 8 -
                  (REMAP ? 0 : 256 * GS);      // slot id s lives in row s - 1 (id 0 is "no operand")
@@ -1779,7 +1825,7 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tb = s_tmem + ((uint32_t(warp & 3) * 32u) << 16) + uint32_t(warp >> 2) * uint32_t(2 * n_rows) - 2u;
+        tb = s_tmem + ((uint32_t(warp & 3) * 32u) << 16) + uint32_t(warp >> 2) * uint32_t(G * n_rows) - uint32_t(G);
     }
     const uint64_t* const arena = a.arena;
     unsigned long long st_tiles = 0, st_cells = 0, st_items = 0;
@@ -1789,7 +1835,7 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
     const int size = tps * 8;
     const float recip = 1.0f / float(tps * 8u);
     const float* m = mat.d;
-    constexpr int SHIFT = TM ? 0 : (G == 4 ? 2 : (G == 2 ? 1 : 0));
+    constexpr int SHIFT = GS == 4 ? 2 : (GS == 2 ? 1 : 0);
 
     for (;;) {
         const int item = warp_next(a.queue);
@@ -1817,10 +1863,10 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
                 slots.st(off_lhs2(h), Y);
                 slots.st(off_rhs2(h), make_float2(a.z, a.z));
             } else {
-                if (TM && g == 1) {                                                     // tile 1: tensor memory
-                    if (off_out2(h)) tm_st2(tb + tm_col(off_out2(h)), X);
-                    if (off_lhs2(h)) tm_st2(tb + tm_col(off_lhs2(h)), Y);
-                    if (off_rhs2(h)) tm_st2(tb + tm_col(off_rhs2(h)), make_float2(a.z, a.z));
+                if (TM && g >= GS) {                                                    // the second half of the tiles: tensor memory
+                    if (off_out2(h)) tm_st2(tb + tm_col(off_out2(h)) + 2 * (g - GS), X);
+                    if (off_lhs2(h)) tm_st2(tb + tm_col(off_lhs2(h)) + 2 * (g - GS), Y);
+                    if (off_rhs2(h)) tm_st2(tb + tm_col(off_rhs2(h)) + 2 * (g - GS), make_float2(a.z, a.z));
                 } else {
                     if (off_out2(h)) sts_f2(slots.base + off_out2(h) + 8 * g, X);      // id 0: axis unused, no row
                     if (off_lhs2(h)) sts_f2(slots.base + off_lhs2(h) + 8 * g, Y);
@@ -1876,7 +1922,7 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
     Stream ts;
     ts.init(s_dyn + warp * Stream::stride(), a.arena, a.arena_cap);
     const int n_rows = a.n_rows;       // shared-memory value rows per warp (= slot count unless REMAP)
-    constexpr int GS = TM ? 1 : G;     // tiles whose rows live in shared memory
+    constexpr int GS = TM ? G / 2 : G; // tiles whose rows live in shared memory (TM: the other half in tensor memory)
     Slots2<REMAP> slots;
     slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * GS) * 8 -
                  (REMAP ? 0 : 256 * GS);      // slot id s lives in row s - 1 (id 0 is "no operand")
@@ -1896,7 +1942,7 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tb = s_tmem + ((uint32_t(warp & 3) * 32u) << 16) + uint32_t(warp >> 2) * uint32_t(2 * n_rows) - 2u;
+        tb = s_tmem + ((uint32_t(warp & 3) * 32u) << 16) + uint32_t(warp >> 2) * uint32_t(G * n_rows) - uint32_t(G);
     }
     const uint64_t* const arena = a.arena;
     unsigned long long st_tiles = 0, st_cells = 0, st_items = 0;
@@ -1906,7 +1952,7 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
     const int size = tps * 4;
     const float recip = 1.0f / float(tps * 4u);
     const float* m = mat.d;
-    constexpr int SHIFT = TM ? 0 : (G == 4 ? 2 : (G == 2 ? 1 : 0));
+    constexpr int SHIFT = GS == 4 ? 2 : (GS == 2 ? 1 : 0);
 
     for (;;) {
         const int item = warp_next(a.queue);
@@ -1949,10 +1995,10 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
                 slots.st(off_lhs2(hdr), Y);
                 slots.st(off_rhs2(hdr), Z);
             } else {
-                if (TM && g == 1) {                                                     // tile 1: tensor memory
-                    if (off_out2(hdr)) tm_st2(tb + tm_col(off_out2(hdr)), X);
-                    if (off_lhs2(hdr)) tm_st2(tb + tm_col(off_lhs2(hdr)), Y);
-                    if (off_rhs2(hdr)) tm_st2(tb + tm_col(off_rhs2(hdr)), Z);
+                if (TM && g >= GS) {                                                    // the second half of the tiles: tensor memory
+                    if (off_out2(hdr)) tm_st2(tb + tm_col(off_out2(hdr)) + 2 * (g - GS), X);
+                    if (off_lhs2(hdr)) tm_st2(tb + tm_col(off_lhs2(hdr)) + 2 * (g - GS), Y);
+                    if (off_rhs2(hdr)) tm_st2(tb + tm_col(off_rhs2(hdr)) + 2 * (g - GS), Z);
                 } else {
                     if (off_out2(hdr)) sts_f2(slots.base + off_out2(hdr) + 8 * g, X);  // id 0: axis unused, no row
                     if (off_lhs2(hdr)) sts_f2(slots.base + off_lhs2(hdr) + 8 * g, Y);
@@ -2223,7 +2269,13 @@ bool float_tmem(int n_slots, bool heat) {
 }
 int float_group(int n_slots, bool heat) {
     if (use_remap(n_slots) || heat) return 1;
-    if (float_tmem(n_slots, heat)) return 2;
+    if (float_tmem(n_slots, heat)) {
+        // MPRB_FLOAT_TMEM_GROUP=4: four tiles per item, two in shared memory and two in tensor memory - the same
+        // fetch / decode / branch / loads / store serve four tiles (items fill to 3.7 tiles on bear), but only 19
+        // warps fit an SM and the walk becomes latency-bound: bear 1024^3 float pass 5.05 ms against 3.59 ms
+        static const char* tg = getenv("MPRB_FLOAT_TMEM_GROUP");
+        return (tg && tg[0] == '4') ? 4 : 2;
+    }
     static const char* env = getenv("MPRB_FLOAT_GROUP");
     if (env) { const int v = atoi(env); return v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
     return 1;
@@ -2244,7 +2296,7 @@ static FloatShape float_shape(int n_slots, int group, bool tmem) {
         cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     }
     const int rows = walk_rows(n_slots);
-    const size_t per_warp = walk_smem(rows, use_remap(n_slots), 1, tmem ? 1 : group, true);
+    const size_t per_warp = walk_smem(rows, use_remap(n_slots), 1, tmem ? group / 2 : group, true);
     FloatShape best = {1, 1, 32};
     int best_resident = 0;
     for (int w = 1; w <= kFloatMaxThreads / 32; ++w) {
@@ -2254,7 +2306,7 @@ static FloatShape float_shape(int n_slots, int group, bool tmem) {
         if (ctas > 64 / w) ctas = 64 / w;
         int cols = 32;
         if (tmem) {
-            cols = pow2_at_least(((w + 3) / 4) * 2 * rows);
+            cols = pow2_at_least(((w + 3) / 4) * group * rows);       // half of `group` tiles, two columns each, per slot
             if (cols > 512) continue;
             ctas = std::min(ctas, 512 / cols);
         }
@@ -2286,6 +2338,7 @@ bool use_local_normals(int n_slots) {
 template <typename F> static auto pick_float(int G, bool tmem, F f) {
     typedef std::integral_constant<bool, true> T;
     typedef std::integral_constant<bool, false> N;
+    if (tmem && G == 4) return f(std::integral_constant<int, 4>(), T());
     if (tmem) return f(std::integral_constant<int, 2>(), T());
     if (G == 4) return f(std::integral_constant<int, 4>(), N());
     if (G == 2) return f(std::integral_constant<int, 2>(), N());
@@ -2328,7 +2381,7 @@ void init_kernels(int max_smem_optin) {
     opt_in(k_eval_pixels<true, true>, max_smem_optin);
     opt_in(k_eval_voxels<true, true>, max_smem_optin);
     for (int G = 1; G <= 4; G *= 2)
-        for (int T = 0; T <= (G == 2 ? 1 : 0); ++T)
+        for (int T = 0; T <= (G >= 2 ? 1 : 0); ++T)
             pick_float(G, T != 0, [&](auto g, auto t) {
                 opt_in(k_eval_pixels<false, false, decltype(g)::value, decltype(t)::value>, max_smem_optin);
                 opt_in(k_eval_voxels<false, false, decltype(g)::value, decltype(t)::value>, max_smem_optin);
@@ -2409,7 +2462,7 @@ void launch_eval_pixels(const EvalVoxelsArgs& a, const Mat3& mat, int grid, cuda
     const FloatShape sh = float_shape(a.n_slots, G, tm);
     EvalVoxelsArgs b = a;
     b.tmem_cols = sh.tmem_cols;
-    size_t smem = walk_smem(a.n_rows, local, sh.warps, tm ? 1 : G, true);
+    size_t smem = walk_smem(a.n_rows, local, sh.warps, tm ? G / 2 : G, true);
     if (tm) smem = std::max(smem, float_pad_smem(sh));
     const int fw = sh.warps;
     if (a.heat) {
@@ -2429,7 +2482,7 @@ void launch_eval_voxels(const EvalVoxelsArgs& a, const Mat4& mat, int grid, cuda
     const FloatShape sh = float_shape(a.n_slots, G, tm);
     EvalVoxelsArgs b = a;
     b.tmem_cols = sh.tmem_cols;
-    size_t smem = walk_smem(a.n_rows, local, sh.warps, tm ? 1 : G, true);
+    size_t smem = walk_smem(a.n_rows, local, sh.warps, tm ? G / 2 : G, true);
     if (tm) smem = std::max(smem, float_pad_smem(sh));
     const int fw = sh.warps;
     if (a.heat) {

@@ -104,7 +104,7 @@ enum { PL_N = 0,          // clauses of the shortened tape (logical cells 1 .. n
        PL_LOGICAL = 4,    // its logical cell count, n + 2
        PL_VALUES = 5,     // value ids in use: 4 + n + forwarding nodes
        PL_SCHED = 6,      // word offset of the clause array from the plan's first word
-       PL_COUNT = 7 };    // entries in the clause array (n + forwarding nodes)
+       PL_EXTRAS = 7 };   // copies that keep a second source alive: (cell | source << 16) words behind the clause array
 constexpr int kPlanHeader = 8;
 constexpr int kPlanMaxClauses = 4000;   // < kMaxChoices: every verdict of a planned tape is recorded
 constexpr int kPlanMinClauses = 160;    // shorter tapes are walked serially faster than their levels can be swept

@@ -492,7 +492,7 @@ def test_generated_interval_loop_runs_whole_tapes_like_the_c_restatement():
 
 
 @pytest.mark.parametrize("G,inc", [(1, "float_loop_ptx.inc"), (2, "float_loop_ptx_g2.inc"), (4, "float_loop_ptx_g4.inc"),
-                                   (2, "float_loop_ptx_g2t.inc")])
+                                   (2, "float_loop_ptx_g2t.inc"), (4, "float_loop_ptx_g4t.inc")])
 def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation(G, inc):
     """Same for the float pass's loops (G tiles per warp, two samples per tile and lane; slot bytes
     pre-multiplied by G as annotate_chunk does), against numpy float32 arithmetic with the
@@ -508,9 +508,10 @@ def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation(G, 
     rng = np.random.default_rng(5)
     CH, SB, TB = 0x1000, 0x4000, 0x40
     f32 = np.float32
-    TM = inc.endswith("g2t.inc")      # tile 0 in shared-memory rows of 256 bytes, tile 1 in tensor-memory columns 2 s, 2 s + 1
-    TT = inc.endswith("g2tt.inc")     # both tiles in tensor memory: columns 4 s .. 4 s + 3, slot bytes pre-multiplied by 4
-    GS = 4 if TT else (1 if TM else G)   # what annotate_chunk multiplies the slot bytes by
+    # ...t.inc: the first G / 2 tiles in shared-memory rows (G / 2 tiles wide), the others in tensor memory,
+    # slot s = columns G s .. G s + G - 1 (two per tile)
+    TM = inc.endswith("t.inc")
+    GS = G // 2 if TM else G          # tiles per shared-memory row = what annotate_chunk multiplies the slot bytes by
 
     def clause(op, l, r, imm):
         with np.errstate(all="ignore"):
@@ -540,14 +541,11 @@ def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation(G, 
         m = LoopMachine(asm, {"cp": CH - 8, "sb": SB, "tb": TB, "w": 0, "imm": 0},
                         {"%0": "cp", "%1": "w", "%2": "imm", "%3": "sb", "%4": "tb"}, smem)
         for s, v in slots.items():
-            if TT:
-                for k in range(4):
-                    m.tmem[TB + 4 * s + k] = f2b(v[k])
-                continue
             for k in range(2 * GS):
                 smem[SB + 256 * GS * s + 4 * k] = f2b(v[k])
             if TM:
-                m.tmem[TB + 2 * s], m.tmem[TB + 2 * s + 1] = f2b(v[2]), f2b(v[3])
+                for k in range(G):
+                    m.tmem[TB + G * s + k] = f2b(v[G + k])
         m.execute()
         assert m.r["cp"] == CH + 8 * n and (m.r["w"] & 0xff) == 0
         for c in cells[:-1]:
@@ -555,13 +553,9 @@ def test_generated_float_loop_runs_whole_tapes_like_plain_float32_evaluation(G, 
             imm = b2f(c >> 32)
             slots[out] = np.array([clause(op, slots[lhs][k], slots[rhs][k], imm) for k in range(2 * G)], dtype=f32)
         for s, v in slots.items():
-            if TT:
-                got = np.array([b2f(m.tmem[TB + 4 * s + k]) for k in range(4)], dtype=f32)
-                assert ((got == v) | (np.isnan(got) & np.isnan(v))).all(), (trial, s, got, v)
-                continue
             got = [b2f(smem[SB + 256 * GS * s + 4 * k]) for k in range(2 * GS)]
             if TM:
-                got += [b2f(m.tmem[TB + 2 * s]), b2f(m.tmem[TB + 2 * s + 1])]
+                got += [b2f(m.tmem[TB + G * s + k]) for k in range(G)]
             got = np.array(got, dtype=f32)
             assert ((got == v) | (np.isnan(got) & np.isnan(v))).all(), (trial, s, got, v)
 
