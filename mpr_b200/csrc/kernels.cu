@@ -837,15 +837,19 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
     const int32_t* __restrict__ const ls = a.level_start;
     const int nl = a.n_levels;
     int k0 = ls[0], k1 = ls[1], k2 = ls[min(2, nl)];
-    RootClause nxt = {};
+    RootClause nxt = {}, nxt2 = {};            // a level is often a little wider than the group: two clauses ahead
     if (k0 + t < k1) nxt = a.sched[k0 + t];
+    if (k0 + G + t < k1) nxt2 = a.sched[k0 + G + t];
     for (int L = 0; L < nl; ++L) {
         const int k_end = k1;
         RootClause rc = nxt;
+        const RootClause rc2 = nxt2;
         const int k3 = ls[min(L + 3, nl)];
         if (k1 + t < k2) nxt = a.sched[k1 + t];
+        if (k1 + G + t < k2) nxt2 = a.sched[k1 + G + t];
         for (int k = k0 + t; k < k_end; k += G) {
-            if (k >= k0 + G) rc = a.sched[k];
+            if (k >= k0 + 2 * G) rc = a.sched[k];
+            else if (k >= k0 + G) rc = rc2;
             const uint32_t op = rc.op_idx & 0xff;
             const uint32_t idx = rc.op_idx >> 12;
             const float imm = rc.imm;
@@ -904,14 +908,18 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
         group_sync(bar, G);
         {
             int e1 = ls[nl], e0 = ls[nl - 1], em = ls[max(nl - 2, 0)];      // level L is [e0, e1), level L - 1 [em, e0)
-            RootClause ahead = {};
+            RootClause ahead = {}, ahead2 = {};
             if (e0 + t < e1) ahead = a.sched[e0 + t];
+            if (e0 + G + t < e1) ahead2 = a.sched[e0 + G + t];
             for (int L = nl - 1; L >= 0; --L) {
                 RootClause rc = ahead;
+                const RootClause rc2 = ahead2;
                 const int emm = ls[max(L - 2, 0)];
                 if (L > 0 && em + t < e0) ahead = a.sched[em + t];
+                if (L > 0 && em + G + t < e0) ahead2 = a.sched[em + G + t];
                 for (int k = e0 + t; k < e1; k += G) {
-                    if (k >= e0 + G) rc = a.sched[k];
+                    if (k >= e0 + 2 * G) rc = a.sched[k];
+                    else if (k >= e0 + G) rc = rc2;
                     const uint32_t op = rc.op_idx & 0xff;
                     const uint32_t idx = rc.op_idx >> 12;
                     if (!A[3 + idx]) { KS[k] = 0; continue; }
