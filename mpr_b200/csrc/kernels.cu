@@ -831,25 +831,15 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
     group_sync(bar, G);
 
     // ---- forward: one dependency level at a time ---------------------------------------
-    // Level bounds and the first clause of each thread are fetched (L2) two and one levels ahead: the
-    // levels are short, and a chain of dependent global loads per level would cost more than the level.
+    // (every tile of the launch reads the same schedule, so it comes out of L1: fetching it levels ahead was
+    // measured and only cost instructions)
     bool any_choice = false;
     const int32_t* __restrict__ const ls = a.level_start;
     const int nl = a.n_levels;
-    int k0 = ls[0], k1 = ls[1], k2 = ls[min(2, nl)];
-    RootClause nxt = {}, nxt2 = {};            // a level is often a little wider than the group: two clauses ahead
-    if (k0 + t < k1) nxt = a.sched[k0 + t];
-    if (k0 + G + t < k1) nxt2 = a.sched[k0 + G + t];
     for (int L = 0; L < nl; ++L) {
-        const int k_end = k1;
-        RootClause rc = nxt;
-        const RootClause rc2 = nxt2;
-        const int k3 = ls[min(L + 3, nl)];
-        if (k1 + t < k2) nxt = a.sched[k1 + t];
-        if (k1 + G + t < k2) nxt2 = a.sched[k1 + G + t];
-        for (int k = k0 + t; k < k_end; k += G) {
-            if (k >= k0 + 2 * G) rc = a.sched[k];
-            else if (k >= k0 + G) rc = rc2;
+        const int k_end = ls[L + 1];
+        for (int k = ls[L] + t; k < k_end; k += G) {
+            const RootClause rc = a.sched[k];
             const uint32_t op = rc.op_idx & 0xff;
             const uint32_t idx = rc.op_idx >> 12;
             const float imm = rc.imm;
@@ -865,9 +855,6 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
                 C[idx] = (rc.op_idx & 0x100u) ? 0 : uint8_t(c);
             }
         }
-        k0 = k1;
-        k1 = k2;
-        k2 = k3;
         group_sync(bar, G);
     }
     if (any_choice) scratch[0] = 1;                          // benign same-value race
@@ -906,35 +893,21 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
         uint8_t* const KS = mine + size_t(nv) * 6;
         if (t == 0) A[a.result_v] = 1;
         group_sync(bar, G);
-        {
-            int e1 = ls[nl], e0 = ls[nl - 1], em = ls[max(nl - 2, 0)];      // level L is [e0, e1), level L - 1 [em, e0)
-            RootClause ahead = {}, ahead2 = {};
-            if (e0 + t < e1) ahead = a.sched[e0 + t];
-            if (e0 + G + t < e1) ahead2 = a.sched[e0 + G + t];
-            for (int L = nl - 1; L >= 0; --L) {
-                RootClause rc = ahead;
-                const RootClause rc2 = ahead2;
-                const int emm = ls[max(L - 2, 0)];
-                if (L > 0 && em + t < e0) ahead = a.sched[em + t];
-                if (L > 0 && em + G + t < e0) ahead2 = a.sched[em + G + t];
-                for (int k = e0 + t; k < e1; k += G) {
-                    if (k >= e0 + 2 * G) rc = a.sched[k];
-                    else if (k >= e0 + G) rc = rc2;
-                    const uint32_t op = rc.op_idx & 0xff;
-                    const uint32_t idx = rc.op_idx >> 12;
-                    if (!A[3 + idx]) { KS[k] = 0; continue; }
-                    const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[idx] : 0;
-                    // in the shortened tape unless the verdict's operand already sits in the output slot
-                    KS[k] = ((c == 1 && (rc.op_idx & 0x200u)) || (c == 2 && (rc.op_idx & 0x400u))) ? 0 : 1;
-                    if (c == 0) { A[rc.lsrc] = 1; A[rc.rsrc] = 1; }
-                    else if (c == 1) { A[rc.lsrc] = 1; }
-                    else { A[rc.rsrc] = 1; }                     // rsrc == 0 for immediate forms
-                }
-                e1 = e0;
-                e0 = em;
-                em = emm;
-                group_sync(bar, G);
+        for (int L = nl - 1; L >= 0; --L) {
+            const int k_end = ls[L + 1];
+            for (int k = ls[L] + t; k < k_end; k += G) {
+                const RootClause rc = a.sched[k];
+                const uint32_t op = rc.op_idx & 0xff;
+                const uint32_t idx = rc.op_idx >> 12;
+                if (!A[3 + idx]) { KS[k] = 0; continue; }
+                const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[idx] : 0;
+                // in the shortened tape unless the verdict's operand already sits in the output slot
+                KS[k] = ((c == 1 && (rc.op_idx & 0x200u)) || (c == 2 && (rc.op_idx & 0x400u))) ? 0 : 1;
+                if (c == 0) { A[rc.lsrc] = 1; A[rc.rsrc] = 1; }
+                else if (c == 1) { A[rc.lsrc] = 1; }
+                else { A[rc.rsrc] = 1; }                     // rsrc == 0 for immediate forms
             }
+            group_sync(bar, G);
         }
         // ---- sweep: compact kept clauses in tape order ---------------------------------------
         // (a live min / max whose verdict names an operand already sitting in the output slot is dropped,
@@ -1578,11 +1551,14 @@ __global__ void __launch_bounds__(256)
 k_upsample_filled(const int32_t* __restrict__ prev, int32_t* __restrict__ image, int size)
 {
     constexpr int F = (DIM == 3) ? 4 : 8;
-    const int n = size * size;
+    // four pixels of a row per thread (they share their parent tile: 4 divides F): one 16-byte store
+    const int quads = size / 4, n = quads * size;
+    int4* const out = reinterpret_cast<int4*>(image);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int x = i % size, y = i / size;
+        const int x = (i % quads) * 4, y = i / quads;
         const int32_t t = prev[x / F + (y / F) * (size / F)];
-        image[i] = t ? (DIM == 3 ? t * 4 + 3 : 1) : 0;
+        const int32_t v = t ? (DIM == 3 ? t * 4 + 3 : 1) : 0;
+        out[i] = make_int4(v, v, v, v);
     }
 }
 
