@@ -410,9 +410,13 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
     // Root tape to cell 0 of the arena (context.cu:1139-1142), in chunk-terminated layout;
     // pushed tapes start at the next 64-cell boundary so every chunk is 512-byte aligned.
     const int32_t first_free = (n_chunked + kChunk - 1) / kChunk * kChunk;
-    launch_begin_frame(c->ctl, first_free, s);
+    // One launch clears the control block, copies the root tape and clears the level-0 and normal images: the
+    // arena and the images are managed memory, and driver copies / memsets on managed ranges stall the host
+    // (see k_begin_frame).
+    const uint64_t* root_src = td->chunked;
     if (cells_on_host) {
-        // Host-buffer entry points pay the upload every frame: host cells -> pinned staging -> HBM.
+        // Host-buffer entry points pay the upload every frame: host cells -> page-locked staging, which the
+        // kernel reads over PCIe.
         if (c->stage_cells_cap < n_chunked) {
             if (c->stage_cells) cudaFreeHost(c->stage_cells);
             c->stage_cells = nullptr;
@@ -420,14 +424,15 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
             c->stage_cells_cap = n_chunked;
         }
         memcpy(c->stage_cells, plan->host_chunked.data(), sizeof(uint64_t) * size_t(n_chunked));
-        MPRB_CUDA(cudaMemcpyAsync(c->arena, c->stage_cells, sizeof(uint64_t) * size_t(n_chunked),
-                                  cudaMemcpyHostToDevice, s));
-    } else {
-        MPRB_CUDA(cudaMemcpyAsync(c->arena, td->chunked, sizeof(uint64_t) * size_t(n_chunked),
-                                  cudaMemcpyDeviceToDevice, s));
+        root_src = c->stage_cells;
     }
-    MPRB_CUDA(cudaMemsetAsync(c->filled[0], 0, sizeof(int32_t) * size_t(tps0) * tps0, s));
-    if (dim == 3) MPRB_CUDA(cudaMemsetAsync(c->normals, 0, sizeof(uint32_t) * size_t(S) * S, s));
+    {
+        const long long n_normals = dim == 3 ? (long long)S * S : 0;
+        const long long work16 = n_chunked + n_normals / 4 + (long long)tps0 * tps0 / 4;
+        const int grid = int(std::max<long long>(1, std::min<long long>(c->sm_count * 8, (work16 + 255) / 256)));
+        launch_begin_frame(c->ctl, first_free, c->arena, root_src, n_chunked, c->filled[0], (long long)tps0 * tps0,
+                           c->normals, n_normals, grid, s);
+    }
     unsigned long long* heat_units = nullptr;
     if (heat) {
         if (!c->heat_units) MPRB_CUDA(cudaMalloc(&c->heat_units, sizeof(unsigned long long) * size_t(S) * S));
@@ -969,8 +974,13 @@ static int create_one(int32_t image_size_px, const mprb_ctx_opts* opts, mprb_ctx
     if ((e = managed_alloc(&c->arena, size_t(c->arena_cells) + kChunk, device)) != cudaSuccess)
         return bail(e, "tape arena");
     // Host-side mirrors of two device counters (the device copies live in FrameCtl)
-    if ((e = cudaMallocManaged(&c->tape_index, sizeof(int32_t))) != cudaSuccess) return bail(e, "tape_index");
-    if ((e = cudaMallocManaged(&c->num_active_tiles, sizeof(int32_t))) != cudaSuccess)
+    // The two counters the reference keeps in managed memory are written by the HOST after every frame and never
+    // read by a kernel here.  As managed allocations they shared unified-memory pages with small device-side
+    // arrays (stage-0 tiles, level-0 image, tape cells): each host write pulled such a page to the host, the next
+    // frame's first kernel faulted it back (+0.4 ms on a 0.43 ms frame, most frames once the driver's thrashing
+    // heuristics settled).  Page-locked host memory is just as readable through the same pointers.
+    if ((e = cudaMallocHost(&c->tape_index, sizeof(int32_t))) != cudaSuccess) return bail(e, "tape_index");
+    if ((e = cudaMallocHost(&c->num_active_tiles, sizeof(int32_t))) != cudaSuccess)
         return bail(e, "num_active_tiles");
     *c->tape_index = 0;
     *c->num_active_tiles = 0;
@@ -1006,8 +1016,8 @@ void mprb_ctx_destroy(mprb_ctx* c) {
     for (int i = 0; i < 3; ++i) if (c->active_list[i]) cudaFree(c->active_list[i]);
     if (c->float_items) cudaFree(c->float_items);
     if (c->arena) cudaFree(c->arena);
-    if (c->tape_index) cudaFree(c->tape_index);
-    if (c->num_active_tiles) cudaFree(c->num_active_tiles);
+    if (c->tape_index) cudaFreeHost(c->tape_index);
+    if (c->num_active_tiles) cudaFreeHost(c->num_active_tiles);
     if (c->normals) cudaFree(c->normals);
     if (c->ctl) cudaFree(c->ctl);
     if (c->ctl_host) cudaFreeHost(c->ctl_host);
@@ -1315,9 +1325,7 @@ int mprb_effects_draw_ssao(mprb_effects* fx, mprb_ctx* c) {
     if (!fx || !c) return fail(MPRB_E_ARG, "null argument");
     MPRB_CUDA(cudaSetDevice(c->device));
     if (int e = effects_resize(fx, c)) return e;
-    const size_t bytes = sizeof(int32_t) * size_t(c->size) * c->size;
-    MPRB_CUDA(cudaMemsetAsync(fx->tmp, 0, bytes, c->stream));
-    MPRB_CUDA(cudaMemsetAsync(fx->image, 0, bytes, c->stream));
+    launch_clear_pair(fx->tmp, fx->image, (long long)c->size * c->size, c->stream);
     launch_draw_ssao(c->filled[3], c->normals, fx->kernel, fx->rvecs, c->size, fx->tmp, c->stream);
     launch_blur_ssao(c->filled[3], fx->tmp, c->size, fx->image, c->stream);
     MPRB_CUDA(cudaStreamSynchronize(c->stream));
@@ -1328,9 +1336,7 @@ int mprb_effects_draw_shaded(mprb_effects* fx, mprb_ctx* c) {
     if (!fx || !c) return fail(MPRB_E_ARG, "null argument");
     MPRB_CUDA(cudaSetDevice(c->device));
     if (int e = effects_resize(fx, c)) return e;
-    const size_t bytes = sizeof(int32_t) * size_t(c->size) * c->size;
-    MPRB_CUDA(cudaMemsetAsync(fx->tmp, 0, bytes, c->stream));
-    MPRB_CUDA(cudaMemsetAsync(fx->image, 0, bytes, c->stream));
+    launch_clear_pair(fx->tmp, fx->image, (long long)c->size * c->size, c->stream);
     launch_draw_ssao(c->filled[3], c->normals, fx->kernel, fx->rvecs, c->size, fx->image, c->stream);
     launch_blur_ssao(c->filled[3], fx->image, c->size, fx->tmp, c->stream);
     launch_draw_shaded(c->filled[3], c->normals, fx->tmp, c->size, fx->image, c->stream);

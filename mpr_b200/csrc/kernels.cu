@@ -891,6 +891,7 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
         // KS[k] = clause at schedule position k stays in the shortened tape (the values are done with,
         // the flags take the last eighth of their room; a clause's liveness is final when its level is swept)
         uint8_t* const KS = mine + size_t(nv) * 6;
+        const bool want_plan = a.plans != nullptr;             // frames that write no plans skip the bookkeeping
         if (t == 0) A[a.result_v] = 1;
         group_sync(bar, G);
         for (int L = nl - 1; L >= 0; --L) {
@@ -899,10 +900,13 @@ k_eval_root(const EvalRootArgs a, const typename MatOf<DIM>::type mat)
                 const RootClause rc = a.sched[k];
                 const uint32_t op = rc.op_idx & 0xff;
                 const uint32_t idx = rc.op_idx >> 12;
-                if (!A[3 + idx]) { KS[k] = 0; continue; }
+                if (!A[3 + idx]) {
+                    if (want_plan) KS[k] = 0;
+                    continue;
+                }
                 const int c = (op >= OP_MIN_LI && op <= OP_MAX_LR) ? C[idx] : 0;
                 // in the shortened tape unless the verdict's operand already sits in the output slot
-                KS[k] = ((c == 1 && (rc.op_idx & 0x200u)) || (c == 2 && (rc.op_idx & 0x400u))) ? 0 : 1;
+                if (want_plan) KS[k] = ((c == 1 && (rc.op_idx & 0x200u)) || (c == 2 && (rc.op_idx & 0x400u))) ? 0 : 1;
                 if (c == 0) { A[rc.lsrc] = 1; A[rc.rsrc] = 1; }
                 else if (c == 1) { A[rc.lsrc] = 1; }
                 else { A[rc.rsrc] = 1; }                     // rsrc == 0 for immediate forms
@@ -2185,15 +2189,31 @@ k_normals(const NormalsArgs a, const Mat4 mat)
 }
 
 ////////////////////////////////////////////////////////////////////////////////
-// Frame setup: clear the control block and set the arena allocation cursor.
-
-__global__ void k_begin_frame(FrameCtl* ctl, int32_t first_free)
+// Frame setup in ONE launch: clear the control block and set the arena allocation cursor (block 0), copy the
+// root tape to cell 0 of the arena, clear the level-0 image and (3D) the normal image.  The arena and the
+// images are managed memory (the reference exposes them as host-readable pointers); cudaMemcpyAsync /
+// cudaMemsetAsync on managed ranges go through the unified-memory driver and were measured to stall the
+// host for 0.3-0.6 ms every few frames (frames of 0.43 ms came out at 0.86), a kernel that touches pages
+// already resident on the device does not.  `root` may be device memory or page-locked host memory (the
+// host-buffer entry points stage the cells there and the kernel reads them over PCIe).
+__global__ void __launch_bounds__(256)
+k_begin_frame(FrameCtl* ctl, int32_t first_free, uint64_t* __restrict__ arena, const uint64_t* __restrict__ root,
+              int32_t n_root, uint4* __restrict__ image0, int32_t n_image16, int32_t* __restrict__ image0_tail,
+              int32_t n_tail, uint4* __restrict__ normals, long long n_normals16)
 {
-    const int i = threadIdx.x;
-    int32_t* raw = reinterpret_cast<int32_t*>(ctl);
-    for (int k = i; k < int(sizeof(FrameCtl) / 4); k += blockDim.x) raw[k] = 0;
-    __syncthreads();
-    if (i == 0) ctl->tape_cursor = first_free;
+    if (blockIdx.x == 0) {
+        int32_t* raw = reinterpret_cast<int32_t*>(ctl);
+        for (int k = threadIdx.x; k < int(sizeof(FrameCtl) / 4); k += blockDim.x) raw[k] = 0;
+        __syncthreads();
+        if (threadIdx.x == 0) ctl->tape_cursor = first_free;
+    }
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = t; i < n_root; i += stride) arena[i] = root[i];
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (long long i = t; i < n_image16; i += stride) image0[i] = zero;
+    if (t < n_tail) image0_tail[t] = 0;
+    for (long long i = t; i < n_normals16; i += stride) normals[i] = zero;
 }
 
 // Brute-force frames (reference preload_tiles, context.cu:45-57): every 8x8 tile goes straight
@@ -2496,8 +2516,14 @@ void launch_heat_finish(const unsigned long long* units, float* heat, long long 
     k_heat_finish<<<grid, 256, 0, s>>>(units, heat, n, n_clauses);
 }
 
-void launch_begin_frame(FrameCtl* ctl, int32_t first_free, cudaStream_t s) {
-    k_begin_frame<<<1, 64, 0, s>>>(ctl, first_free);
+void launch_begin_frame(FrameCtl* ctl, int32_t first_free, uint64_t* arena, const uint64_t* root, int32_t n_root_cells,
+                        int32_t* image0, long long n_image0, uint32_t* normals, long long n_normals, int grid,
+                        cudaStream_t s) {
+    // the level-0 image has (size / 64)^d entries, a multiple of 4 only from 128 px on: its tail (< 4 entries)
+    // is cleared one entry at a time
+    const long long n16 = n_image0 / 4;
+    k_begin_frame<<<grid, 256, 0, s>>>(ctl, first_free, arena, root, n_root_cells, reinterpret_cast<uint4*>(image0), int32_t(n16), image0 + n16 * 4,
+                                       int32_t(n_image0 - n16 * 4), reinterpret_cast<uint4*>(normals), n_normals / 4);
 }
 
 template <typename K>

@@ -192,7 +192,11 @@ void launch_preload_tiles(TileNode* tiles, int32_t* items, int32_t count, int32_
                           cudaStream_t s);
 void launch_heat_finish(const unsigned long long* units, float* heat, long long n, int32_t n_clauses, int grid,
                         cudaStream_t s);
-void launch_begin_frame(FrameCtl* ctl, int32_t first_free, cudaStream_t s);
+// clears the control block, copies the root tape to cell 0 of the arena and clears
+// the level-0 image and the normal image (n_normals: 0 in 2D, else a multiple of 4) - one launch, no driver memset
+void launch_begin_frame(FrameCtl* ctl, int32_t first_free, uint64_t* arena, const uint64_t* root, int32_t n_root_cells,
+                        int32_t* image0, long long n_image0, uint32_t* normals, long long n_normals, int grid,
+                        cudaStream_t s);
 void launch_eval_tiles(int dim, bool root, const EvalTilesArgs& a, const void* mat, int grid, cudaStream_t s);
 void launch_eval_root(int dim, const EvalRootArgs& a, const void* mat, cudaStream_t s);
 // Shared memory a tile of k_eval_sub needs for a plan with nv value ids and n_levels levels.

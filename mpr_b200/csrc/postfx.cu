@@ -188,8 +188,24 @@ __global__ void k_draw_shaded(const int32_t* __restrict__ depth, const uint32_t*
     output[x + y * size] = (0xFF << 24) | (color << 16) | (color << 8) | (color << 0);
 }
 
+// Both result images to zero in one launch (the reference memsets them, effects.cu:265-266 / :283-284; they
+// are managed memory here and a driver memset on a managed range stalls the host, see k_begin_frame).
+__global__ void k_clear_pair(uint4* __restrict__ a, uint4* __restrict__ b, long long n16)
+{
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+        a[i] = zero;
+        b[i] = zero;
+    }
+}
+
 }  // namespace
 
+void launch_clear_pair(int32_t* a, int32_t* b, long long n, cudaStream_t s) {
+    const long long n16 = n / 4;                    // image sizes are multiples of 64 px
+    const int grid = int(n16 / 256 < 1 ? 1 : (n16 / 256 > 148 * 16 ? 148 * 16 : n16 / 256));
+    k_clear_pair<<<grid, 256, 0, s>>>(reinterpret_cast<uint4*>(a), reinterpret_cast<uint4*>(b), n16);
+}
 void launch_draw_ssao(const int32_t* depth, const uint32_t* norm, const float* kernel, const float* rvecs,
                       int size, int32_t* out, cudaStream_t s) {
     const unsigned u = (size + 15) / 16;

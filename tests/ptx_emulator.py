@@ -3,8 +3,9 @@
 with IEEE directed rounding done in exact rational arithmetic.  Test infrastructure only.
 
 Registers hold raw 32-bit patterns; float instructions reinterpret them.  Supported: mov, neg, abs,
-add/sub/mul/div/sqrt with .rm / .rp / .rn, min, max, setp (f32 and u32), selp, and/or/not on
-predicates, and/or/shl/shr/add on b32, mad.wide.u32, predicated st.u32 / mov (the verdict record)."""
+add/sub/mul/div/sqrt with .rm / .rp / .rn, fma.rn, mul.ftz, rcp / rsqrt.approx (modelled as the correctly
+rounded value moved by APPROX_ULPS units), min, max, setp (f32 and u32, with a combining predicate), the
+warp vote of one lane, selp, and/or/not on predicates, and/or/shl/shr/add on b32, mad.wide.u32, predicated st.u32 / mov (the verdict record)."""
 from __future__ import annotations
 
 import math
@@ -137,6 +138,58 @@ def fsqrt(a, mode):
     return c if mid * mid > x else n
 
 
+def ffma(a, b, c):
+    """fma.rn.f32 on finite operands (the hand-expanded sqrt / division sequences of the float loop):
+    one rounding of the exact a b + c."""
+    a, b, c = np.float32(a), np.float32(b), np.float32(c)
+    if not (np.isfinite(a) and np.isfinite(b) and np.isfinite(c)):
+        with np.errstate(all="ignore"):
+            return np.float32(np.float64(a) * np.float64(b) + np.float64(c))   # NaN / infinity propagation only
+    s = Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c))
+    if s == 0:
+        pneg = bool(np.signbit(a)) != bool(np.signbit(b))
+        return _zero(pneg and bool(np.signbit(c)))
+    return _round(s, "rn")
+
+
+# MUFU.RCP / MUFU.RSQ are approximations (about one unit in the last place); the sequences built on them
+# must give the correctly rounded result for ANY value that close, so the model returns the correctly
+# rounded value moved by APPROX_ULPS units - tests run the loops with -1, 0 and +1.
+APPROX_ULPS = 0
+
+
+def _nudge(x: np.float32) -> np.float32:
+    for _ in range(abs(APPROX_ULPS)):
+        x = np.nextafter(x, np.float32(np.inf if APPROX_ULPS > 0 else -np.inf))
+    return x
+
+
+def _ftz(x: np.float32) -> np.float32:
+    x = np.float32(x)
+    if x != 0 and np.isfinite(x) and abs(x) < np.finfo(np.float32).tiny:
+        return _zero(bool(np.signbit(x)))
+    return x
+
+
+def frcp_approx(a):
+    a = _ftz(a)
+    if np.isnan(a) or a == 0 or np.isinf(a):
+        with np.errstate(all="ignore"):
+            return np.float32(1.0) / a
+    return _ftz(_nudge(fdiv(np.float32(1.0), a, "rn")))
+
+
+def frsqrt_approx(a):
+    a = _ftz(a)
+    if np.isnan(a) or a < 0:
+        return np.float32(np.nan)
+    if a == 0:
+        return np.float32(np.inf)
+    if np.isinf(a):
+        return np.float32(0.0)
+    return _ftz(_nudge(np.float32(1.0 / math.sqrt(float(a)))))     # double precision, then one rounding: within half a unit
+
+
 def fmin(a, b):
     a, b = np.float32(a), np.float32(b)
     if np.isnan(a):
@@ -212,6 +265,21 @@ class Machine:
                 x, y = f(1), f(2)
                 c = op.split(".")[1]
                 self.set(a[0], bool({"lt": x < y, "gt": x > y, "le": x <= y, "ge": x >= y, "eq": x == y, "ne": x != y}[c]))
+            elif re.fullmatch(r"setp\.(lt|gt|le|ge|eq|ne)\.(or|and)\.u32", op):
+                x, y = self.val(a[1]), self.val(a[2])
+                c, bop = op.split(".")[1:3]
+                t = {"lt": x < y, "gt": x > y, "le": x <= y, "ge": x >= y, "eq": x == y, "ne": x != y}[c]
+                self.set(a[0], (t or bool(self.r[a[3]])) if bop == "or" else (t and bool(self.r[a[3]])))
+            elif op == "vote.sync.any.pred":
+                self.set(a[0], bool(self.r[a[1]]))          # one lane stands for the warp
+            elif op == "fma.rn.f32":
+                self.set(a[0], f2b(ffma(f(1), f(2), f(3))))
+            elif op == "mul.ftz.f32":
+                self.set(a[0], f2b(_ftz(fmul(_ftz(f(1)), _ftz(f(2)), "rn"))))
+            elif op == "rcp.approx.ftz.f32":
+                self.set(a[0], f2b(frcp_approx(f(1))))
+            elif op == "rsqrt.approx.ftz.f32":
+                self.set(a[0], f2b(frsqrt_approx(f(1))))
             elif re.fullmatch(r"setp\.(lt|gt|le|ge|eq|ne)\.u32", op):
                 x, y = self.val(a[1]), self.val(a[2])
                 c = op.split(".")[1]

@@ -576,3 +576,54 @@ def test_planned_marking_keeps_the_clauses_the_reference_slot_walk_keeps(model):
         most_sweeps = max(most_sweeps, sweeps)
     if model == "prospero":
         assert most_sweeps >= 2
+
+
+@pytest.mark.parametrize("ulps", [-2, -1, 0, 1, 2])
+def test_hand_expanded_sqrt_and_division_by_an_immediate_round_like_ieee(ulps):
+    """The float loops expand sqrt and x / immediate themselves (tools/gen_float_loop.py, sqrt_fast /
+    div_imm_fast: one range vote for all elements of a clause, the reciprocal refined once).  The clause
+    semantics are the reference's `sqrtf(lhs)` and `lhs / imm` (context.cu:887-920), i.e. IEEE-754
+    correctly rounded results - here for operands inside and outside the fast range (outside, the loop
+    falls back to sqrt.rn / div.rn), with the hardware approximations MUFU.RSQ / MUFU.RCP modelled as
+    the correctly rounded value moved by `ulps` units in the last place."""
+    import ptx_emulator
+    from ptx_emulator import LoopMachine, b2f, f2b, load_asm
+    asm = load_asm(ROOT / "mpr_b200" / "csrc" / "float_loop_ptx.inc")
+    rng = np.random.default_rng(11 + ulps)
+    f32 = np.float32
+    CH, SB = 0x1000, 0x4000
+
+    def rnd(lo, hi, signed):
+        m = rng.integers(0, 1 << 23)
+        if rng.random() < 0.15:
+            m = int(rng.choice([0, 1, (1 << 23) - 1, (1 << 23) - 2, 1 << 22, (1 << 22) + 1, (1 << 22) - 1]))
+        bits = (int(rng.integers(lo, hi + 1)) + 127) << 23 | int(m)
+        if signed and rng.random() < 0.5:
+            bits |= 0x80000000
+        return b2f(bits)
+
+    ptx_emulator.APPROX_ULPS = ulps
+    try:
+        for trial in range(400):
+            wide = trial % 4 == 3                                # every fourth case leaves the fast range
+            imm = rnd(-80, 80, True) if wide else rnd(-60, 60, True)
+            a = [rnd(-110, 110, False) if wide else rnd(-100, 100, False) for _ in range(2)]   # sqrt operands
+            d = [rnd(-80, 80, True) if wide else rnd(-60, 60, True) for _ in range(2)]         # dividends
+            if trial % 10 == 9:
+                d[0] = f32(float(imm) * float(rnd(0, 0, False)))                                # quotient near 1
+            cells = [3 | 1 << 8 | 1 << 16, 24 | 2 << 8 | 2 << 16 | f2b(imm) << 32, 0 | 1 << 8]
+            smem = {}
+            for j, c in enumerate(cells):
+                smem[CH + 8 * j], smem[CH + 8 * j + 4] = c & 0xffffffff, c >> 32
+            for k in range(2):
+                smem[SB + 256 * 1 + 4 * k] = f2b(a[k])
+                smem[SB + 256 * 2 + 4 * k] = f2b(d[k])
+            m = LoopMachine(asm, {"cp": CH - 8, "sb": SB, "tb": 0, "w": 0, "imm": 0},
+                            {"%0": "cp", "%1": "w", "%2": "imm", "%3": "sb", "%4": "tb"}, smem)
+            m.execute()
+            with np.errstate(all="ignore"):
+                for k in range(2):
+                    assert smem[SB + 256 + 4 * k] == f2b(np.sqrt(f32(a[k]))), (trial, k, a[k])
+                    assert smem[SB + 512 + 4 * k] == f2b(f32(d[k]) / f32(imm)), (trial, k, d[k], imm)
+    finally:
+        ptx_emulator.APPROX_ULPS = 0
