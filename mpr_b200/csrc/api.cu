@@ -656,7 +656,7 @@ int render(mprb_ctx* c, int dim, const mprb_tape* plan, bool cells_on_host, cons
         va.ctl = c->ctl;
         va.queue = &c->ctl->queue[q++];
         va.n_slots = n_slots;
-        va.n_rows = walk_rows(n_slots);
+        va.n_rows = float_rows(n_slots);
         va.z = z;
         va.heat = heat_units;
         va.n_root = n_cells - 2;

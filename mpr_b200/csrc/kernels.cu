@@ -1723,16 +1723,16 @@ __device__ __forceinline__ void walk_float(TapeStream<REMAP, REMAP>& ts, int tap
     uint32_t w, immb;
     for (;;) {
         if (REMAP) {
-            cp += 8;
-            const uint2 d = lds_u2(cp);
-            w = d.x;
-            immb = d.y;
+            // the generated loop on the renamed chunk (no forwarding hints there: every handler loads its
+            // operands and stores its result); clauses that touch a spilled row come back as kOpBounce
+            run_float_clauses<1>(cp, w, immb, slots.base);
         } else if (TM) {
             run_float_clauses_tm<G>(cp, w, immb, slots.base, tb);
         } else {
             run_float_clauses<G>(cp, w, immb, slots.base);
         }
-        const uint32_t op = w & 0xff;
+        uint32_t op = w & 0xff;
+        if (REMAP && op == kOpBounce) op = lds_u32(cp - ts.rd + ts.buf) & 0xff;      // its opcode, from the raw chunk
         if (op <= OP_JUMP) {
             cells += (cp - seg) >> 3;
             if (op == OP_END) { --cells; break; }
@@ -1798,6 +1798,7 @@ k_eval_pixels(const EvalVoxelsArgs a, const Mat3 mat)
     slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * GS) * 8 -
                  (REMAP ? 0 : 256 * GS);      // slot id s lives in row s - 1 (id 0 is "no operand")
     slots.limit = uint32_t(n_rows) * 256u;
+    if (REMAP) { ts.row_limit = uint32_t(n_rows); ts.bounce_ops = kFastOps; }   // clauses on spilled rows leave the generated loop
     // TM: tile 1's value rows live in tensor memory.  Warp w owns TMEM lanes 32 (w % 4) .. + 31 (the
     // hardware's rule) and the column group w / 4 of the CTA's allocation, 2 n_rows columns wide.
     uint32_t tb = 0;
@@ -1915,6 +1916,7 @@ k_eval_voxels(const EvalVoxelsArgs a, const Mat4 mat)
     slots.base = smem_addr(s_dyn + (blockDim.x >> 5) * Stream::stride()) + ((warp * n_rows * 32 + lane) * GS) * 8 -
                  (REMAP ? 0 : 256 * GS);      // slot id s lives in row s - 1 (id 0 is "no operand")
     slots.limit = uint32_t(n_rows) * 256u;
+    if (REMAP) { ts.row_limit = uint32_t(n_rows); ts.bounce_ops = kFastOps; }   // clauses on spilled rows leave the generated loop
     // TM: tile 1's value rows live in tensor memory.  Warp w owns TMEM lanes 32 (w % 4) .. + 31 (the
     // hardware's rule) and the column group w / 4 of the CTA's allocation, 2 n_rows columns wide.
     uint32_t tb = 0;
@@ -2259,6 +2261,16 @@ int walk_rows(int n_slots) {
     const int rows = env ? atoi(env) : kRemapRowsDefault;
     return rows < kRemapRowsMin ? kRemapRowsMin : (rows > 128 ? 128 : rows);
 }
+// Shared-memory value rows per warp of the FLOAT pass.  With renamed slots its clause loop is the generated
+// one, which only runs clauses whose rows are all in shared memory (the others bounce through C++ with the
+// spilling accessors), so it wants more rows than the interval pass, whose C++ walker spills by itself.
+// MPRB_FLOAT_ROWS overrides.
+int float_rows(int n_slots) {
+    if (!use_remap(n_slots)) return walk_rows(n_slots);
+    static const char* env = getenv("MPRB_FLOAT_ROWS");
+    const int rows = env ? atoi(env) : kFloatRemapRowsDefault;
+    return std::min(std::max(rows, kRemapRowsMin), std::min(n_slots, 128));
+}
 // Tiles per work item of the float pass (1, 2 or 4).  Tiles of an item share their tape, and the
 // clause loop is bound by fetch + dispatch, so G tiles cost little more than one - but slot rows
 // grow G-fold and with them the shared memory per warp.  MPRB_FLOAT_GROUP overrides.
@@ -2299,7 +2311,7 @@ static FloatShape float_shape(int n_slots, int group, bool tmem) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     }
-    const int rows = walk_rows(n_slots);
+    const int rows = float_rows(n_slots);
     const size_t per_warp = walk_smem(rows, use_remap(n_slots), 1, tmem ? group / 2 : group, true);
     FloatShape best = {1, 1, 32};
     int best_resident = 0;

@@ -213,6 +213,7 @@ void launch_normals(const NormalsArgs& a, const Mat4& mat, int grid, cudaStream_
 
 // Resident CTAs per SM for a given slot count (sizes the persistent grids).
 int walk_rows(int n_slots);
+int float_rows(int n_slots);     // value rows per warp of the float pass
 int float_group(int n_slots, bool heat);
 bool float_tmem(int n_slots, bool heat);
 int float_ctas(int dim, int n_slots, int group, bool tmem);

@@ -41,6 +41,8 @@
 namespace mprb {
 
 constexpr int kRemapRowsDefault = 16;           // shared-memory value rows per warp in REMAP mode
+constexpr uint32_t kOpBounce = 31;              // no opcode of the reference (inc/gpu_opcode.hpp: 0..29); see TapeStream::row_limit
+constexpr int kFloatRemapRowsDefault = 16;      // float pass with renamed slots (generated loop): MPRB_FLOAT_ROWS overrides
 constexpr int kRemapRowsMin = 8;                //   (MPRB_REMAP_ROWS overrides; rows beyond spill to local memory)
 // Multiples of 128 bytes: the value rows that follow the streams in shared memory are 256-byte lines
 // read by a whole warp, and a misaligned line costs a third wavefront per access.
@@ -89,6 +91,9 @@ struct TapeStream {
     uint32_t table;          // REMAP: slot id -> row, 256 bytes, 0xFF = not seen yet
     uint32_t parity;         // bit k: phase parity the next wait on buffer k has to see
     uint32_t next_row;       // REMAP: rows handed out so far for the current tape
+    uint32_t row_limit;      // REMAP: clauses of the generated loops that touch a row >= row_limit get opcode
+                             //   kOpBounce in the renamed copy (0xffffffff: never - the C++ walkers spill by themselves)
+    uint32_t bounce_ops;     // REMAP: bit i = opcode i runs in the generated loop (only those are ever bounced)
     int base;                // arena index of cell 0 of `buf` (multiple of 64), or -1
     int pre_base;            // arena index of the chunk requested into `other`, or -1 (a request is always waited
                              // for before its buffer or barrier is used again)
@@ -109,6 +114,8 @@ struct TapeStream {
         table = bars + 16 + 512;
         parity = 0;
         next_row = 0;
+        row_limit = 0xffffffffu;
+        bounce_ops = 0;
         base = -1;
         pre_base = -1;
         cap = arena_cells;
@@ -279,7 +286,10 @@ struct TapeStream {
                 const uint32_t r1 = lds_u8(table + ((w >> 8) & 0xff));
                 const uint32_t r2 = lds_u8(table + ((w >> 16) & 0xff));
                 const uint32_t r3 = lds_u8(table + (w >> 24));
-                w = (w & 0xff) | (r1 << 8) | (r2 << 16) | (r3 << 24);
+                // a clause of the generated loop whose rows are not all shared-memory rows leaves the loop: the
+                // walker takes its opcode from the raw chunk and runs it with the spilling row accessors
+                const uint32_t op = ((bounce_ops >> (w & 31)) & 1u) && max(r1, max(r2, r3)) >= row_limit ? kOpBounce : (w & 0xff);
+                w = op | (r1 << 8) | (r2 << 16) | (r3 << 24);
             }
             sts_u2(rd + (lane + 32 * k) * 8, make_uint2(w, c[k].y));
         }
