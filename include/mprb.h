@@ -53,8 +53,8 @@ typedef struct mprb_buffers {
     mprb_tile_node* tiles[4];     /* stages[i].tiles */
     uint64_t tile_array_size[4];  /* stages[i].tile_array_size: entries valid after the last frame */
     uint64_t* tape_data;          /* subtape arena; the root tape is at cell 0 */
-    int32_t* tape_index;          /* cells of the arena in use after the last frame */
-    int32_t* num_active_tiles;    /* survivors of the last interval level */
+    int32_t* tape_index;          /* cells of the arena in use after the last frame (page-locked host memory) */
+    int32_t* num_active_tiles;    /* survivors of the last interval level (page-locked host memory) */
     uint32_t* normals;            /* 0xFFzzyyxx per pixel (3D only) */
 } mprb_buffers;
 

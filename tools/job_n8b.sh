@@ -1,0 +1,6 @@
+set -x
+O=gpurun_out/r2n8b; mkdir -p $O
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 10 --warmup 3 > $O/bench_n8.json 2> $O/bench_n8.err
+tail -c 400 $O/bench_n8.json; grep -c "nranks" $O/bench_n8.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 4 --steps 10 --warmup 3 > $O/bench_n4.json 2> $O/bench_n4.err
+tail -c 200 $O/bench_n4.json
