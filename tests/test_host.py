@@ -627,3 +627,68 @@ def test_hand_expanded_sqrt_and_division_by_an_immediate_round_like_ieee(ulps):
                     assert smem[SB + 512 + 4 * k] == f2b(f32(d[k]) / f32(imm)), (trial, k, d[k], imm)
     finally:
         ptx_emulator.APPROX_ULPS = 0
+
+
+@pytest.mark.parametrize("model,dim,size", [("involute_gear_3d", 3, 128), ("architecture", 3, 128), ("prospero", 2, 512)])
+def test_rows_numbered_by_liveness_walk_a_tape_like_slot_ids_and_need_far_fewer_rows(model, dim, size):
+    """DESIGN section 9, item 1 (what the models with renamed slots need next): a backward linear scan - the
+    walk a tape push already does with its live-slot set - numbers rows so that a tape needs one per value
+    live at once instead of one per distinct slot id.  On the last-level tapes the CPU restatement produces
+    for the shipped models: walking by rows gives the value walking by slot ids gives, the rows used equal
+    the values live at once (optimal), and they are well under the rows first-sight renaming hands out."""
+    import oracle
+    import row_model
+    cells = load_tape(model)
+    o = oracle.CpuOracle(size)
+    (o.render3D if dim == 3 else o.render2D)(cells)
+    arena = np.ascontiguousarray(o.arena())
+    t = o.tiles(2)
+    tapes = np.unique(t[t["position"] != -1]["tape"])
+    assert len(tapes) > 20
+    rng = np.random.default_rng(3)
+    by_life, by_sight = [], []
+    for tp in rng.choice(tapes, size=min(60, len(tapes)), replace=False):
+        flat = oracle.tape_flatten(arena, int(tp))
+        _, rows, _, n_rows, most = row_model.allocate(flat)
+        assert n_rows == most                                    # never more rows than values live at once
+        assert all(0 < ro <= n_rows and rl <= n_rows and rr <= n_rows for ro, rl, rr in rows)
+        for _ in range(2):
+            xyz = rng.normal(0, 1, 3).astype(np.float32)
+            a, b = row_model.run_by_ids(flat, xyz), row_model.run_by_rows(flat, xyz)
+            assert a == b or (np.isnan(a) and np.isnan(b)), (model, int(tp), a, b)
+        by_life.append(n_rows)
+        by_sight.append(row_model.first_sight_rows(flat))
+    o.close()
+    assert np.mean(by_life) < 0.75 * np.mean(by_sight), (np.mean(by_life), np.mean(by_sight))
+
+
+def test_generated_float_loop_hands_back_clauses_marked_for_the_spilling_path():
+    """With renamed slots TapeStream::rename (tape_stream.cuh) gives a clause that touches a row beyond the
+    shared-memory rows the opcode kOpBounce = 31; the float pass relies on the generated G = 1 loop leaving
+    at such a cell exactly as it leaves at END / JUMP - pointer on the cell, its two words returned, nothing
+    of it executed - and on picking up again behind it (walk_float, kernels.cu)."""
+    from ptx_emulator import LoopMachine, b2f, f2b, load_asm
+    asm = load_asm(ROOT / "mpr_b200" / "csrc" / "float_loop_ptx.inc")
+    text = (ROOT / "mpr_b200" / "csrc" / "tape_stream.cuh").read_text()
+    assert "constexpr uint32_t kOpBounce = 31;" in text
+    CH, SB = 0x1000, 0x4000
+    f32 = np.float32
+    cells = [13 | 1 << 8 | 1 << 16 | f2b(f32(2.0)) << 32,           # s1 = s1 + 2
+             31 | 2 << 8 | 1 << 16 | 3 << 24 | f2b(f32(7.0)) << 32,  # marked: rows 2, 1, 3 (whatever it was)
+             15 | 1 << 8 | 1 << 16 | f2b(f32(3.0)) << 32,           # s1 = s1 * 3
+             0 | 1 << 8]
+    smem = {}
+    for j, c in enumerate(cells):
+        smem[CH + 8 * j], smem[CH + 8 * j + 4] = c & 0xffffffff, c >> 32
+    for k, v in enumerate((1.5, -4.0)):
+        smem[SB + 256 * 1 + 4 * k] = f2b(f32(v))
+        smem[SB + 256 * 2 + 4 * k] = f2b(f32(100.0))
+    regs = {"cp": CH - 8, "sb": SB, "tb": 0, "w": 0, "imm": 0}
+    ops = {"%0": "cp", "%1": "w", "%2": "imm", "%3": "sb", "%4": "tb"}
+    m = LoopMachine(asm, regs, ops, smem).execute()
+    assert m.r["cp"] == CH + 8 and (m.r["w"] & 0xff) == 31 and m.r["w"] >> 8 == 0x030102 and m.r["imm"] == f2b(f32(7.0))
+    assert [b2f(smem[SB + 256 + 4 * k]) for k in range(2)] == [f32(3.5), f32(-2.0)]      # clause 0 ran
+    assert [b2f(smem[SB + 512 + 4 * k]) for k in range(2)] == [f32(100.0), f32(100.0)]   # the marked one did not
+    m = LoopMachine(asm, {**regs, "cp": m.r["cp"]}, ops, smem).execute()                # the walker re-enters behind it
+    assert m.r["cp"] == CH + 24 and (m.r["w"] & 0xff) == 0
+    assert [b2f(smem[SB + 256 + 4 * k]) for k in range(2)] == [f32(10.5), f32(-6.0)]
