@@ -18,8 +18,11 @@
 //   k_eval_voxels             3D float pass: a warp owns one 4x4x4 tile, two voxels per lane
 //   k_eval_root<DIM>          root level, clause-parallel over an SSA / levelised root tape
 //   k_normals                 per-pixel gradient pass, lanes grouped by tape
+//   k_begin_frame             frame setup in one launch: control block, root tape to cell 0 of the arena, image clears
 //   k_preload_tiles, k_heat_finish   brute-force frames and the work meter (analysis variants)
 //
+// With slot renaming (> 32 slot ids) the float pass runs the generated G = 1 loop on the renamed chunk; clauses
+// that touch a row beyond the shared-memory rows come back marked kOpBounce and take the C++ accessors.
 // Without slot renaming (<= 32 slot ids) the clause loops of the interval and float passes are
 // generated PTX (interval_loop_ptx.inc, float_loop_ptx.inc; tools/gen_*_loop.py): one indexed
 // branch per clause, operand forwarding and dead-store elision driven by hint bits that
