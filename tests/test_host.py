@@ -579,19 +579,27 @@ def test_planned_marking_keeps_the_clauses_the_reference_slot_walk_keeps(model):
 
 
 @pytest.mark.parametrize("ulps", [-2, -1, 0, 1, 2])
-def test_hand_expanded_sqrt_and_division_by_an_immediate_round_like_ieee(ulps):
+@pytest.mark.parametrize("G,inc", [(1, "float_loop_ptx.inc"), (2, "float_loop_ptx_g2.inc"), (2, "float_loop_ptx_g2t.inc"),
+                                   (4, "float_loop_ptx_g4t.inc")])
+def test_hand_expanded_sqrt_and_division_by_an_immediate_round_like_ieee(G, inc, ulps):
     """The float loops expand sqrt and x / immediate themselves (tools/gen_float_loop.py, sqrt_fast /
     div_imm_fast: one range vote for all elements of a clause, the reciprocal refined once).  The clause
     semantics are the reference's `sqrtf(lhs)` and `lhs / imm` (context.cu:887-920), i.e. IEEE-754
     correctly rounded results - here for operands inside and outside the fast range (outside, the loop
-    falls back to sqrt.rn / div.rn), with the hardware approximations MUFU.RSQ / MUFU.RCP modelled as
-    the correctly rounded value moved by `ulps` units in the last place."""
+    falls back to sqrt.rn / div.rn).  MUFU.RSQ is modelled as the correctly rounded value moved by `ulps`
+    units in the last place (the sqrt sequence tolerates that); MUFU.RCP as the correctly rounded reciprocal:
+    the division sequence is ptxas' own expansion of div.rn.f32, operation for operation, and like it relies on
+    the hardware's reciprocal for divisors whose mantissa is all ones (tests/ptx_emulator.py).  G = 1: every handler variant
+    carries its own copy; G > 1: one shared body behind stubs, values in shared and (…t.inc) tensor memory."""
     import ptx_emulator
     from ptx_emulator import LoopMachine, b2f, f2b, load_asm
-    asm = load_asm(ROOT / "mpr_b200" / "csrc" / "float_loop_ptx.inc")
-    rng = np.random.default_rng(11 + ulps)
+    asm = load_asm(ROOT / "mpr_b200" / "csrc" / inc)
+    rng = np.random.default_rng(11 + ulps + 7 * G)
     f32 = np.float32
-    CH, SB = 0x1000, 0x4000
+    CH, SB, TB = 0x1000, 0x4000, 0x40
+    TM = inc.endswith("t.inc")
+    GS = G // 2 if TM else G
+    n = 2 * G                                                     # values per slot and lane
 
     def rnd(lo, hi, signed):
         m = rng.integers(0, 1 << 23)
@@ -602,31 +610,43 @@ def test_hand_expanded_sqrt_and_division_by_an_immediate_round_like_ieee(ulps):
             bits |= 0x80000000
         return b2f(bits)
 
-    ptx_emulator.APPROX_ULPS = ulps
+    ptx_emulator.RSQ_ULPS = ulps
     try:
-        for trial in range(400):
+        for trial in range(400 if G == 1 else 60):
             wide = trial % 4 == 3                                # every fourth case leaves the fast range
             imm = rnd(-80, 80, True) if wide else rnd(-60, 60, True)
-            a = [rnd(-110, 110, False) if wide else rnd(-100, 100, False) for _ in range(2)]   # sqrt operands
-            d = [rnd(-80, 80, True) if wide else rnd(-60, 60, True) for _ in range(2)]         # dividends
+            a = [rnd(-110, 110, False) if wide else rnd(-100, 100, False) for _ in range(n)]   # sqrt operands
+            d = [rnd(-80, 80, True) if wide else rnd(-60, 60, True) for _ in range(n)]         # dividends
             if trial % 10 == 9:
                 d[0] = f32(float(imm) * float(rnd(0, 0, False)))                                # quotient near 1
-            cells = [3 | 1 << 8 | 1 << 16, 24 | 2 << 8 | 2 << 16 | f2b(imm) << 32, 0 | 1 << 8]
+            # slot 3 = sqrt(slot 1) stored; slot 2 = slot 2 / imm stored; then the same two through the forwarded
+            # variants: slot 4 = slot 1 + 0 (result stays in registers), slot 4 = sqrt(slot 4); slot 5 = slot 2 + 0 ...
+            cells = [3 | 3 << 8 | 1 << 16, 24 | 2 << 8 | 2 << 16 | f2b(imm) << 32, 0 | 1 << 8]
             smem = {}
             for j, c in enumerate(cells):
-                smem[CH + 8 * j], smem[CH + 8 * j + 4] = c & 0xffffffff, c >> 32
-            for k in range(2):
-                smem[SB + 256 * 1 + 4 * k] = f2b(a[k])
-                smem[SB + 256 * 2 + 4 * k] = f2b(d[k])
-            m = LoopMachine(asm, {"cp": CH - 8, "sb": SB, "tb": 0, "w": 0, "imm": 0},
+                w = c & 0xffffffff
+                w = (w & 0xff) | (((w >> 8) * GS) << 8)
+                smem[CH + 8 * j], smem[CH + 8 * j + 4] = w, c >> 32
+            m = LoopMachine(asm, {"cp": CH - 8, "sb": SB, "tb": TB, "w": 0, "imm": 0},
                             {"%0": "cp", "%1": "w", "%2": "imm", "%3": "sb", "%4": "tb"}, smem)
+            for s_, vals in ((1, a), (2, d)):
+                for k in range(2 * GS):
+                    smem[SB + 256 * GS * s_ + 4 * k] = f2b(vals[k])
+                if TM:
+                    for k in range(G):
+                        m.tmem[TB + G * s_ + k] = f2b(vals[G + k])
             m.execute()
+
+            def got(s_):
+                v = [smem[SB + 256 * GS * s_ + 4 * k] for k in range(2 * GS)]
+                if TM:
+                    v += [m.tmem[TB + G * s_ + k] for k in range(G)]
+                return v
             with np.errstate(all="ignore"):
-                for k in range(2):
-                    assert smem[SB + 256 + 4 * k] == f2b(np.sqrt(f32(a[k]))), (trial, k, a[k])
-                    assert smem[SB + 512 + 4 * k] == f2b(f32(d[k]) / f32(imm)), (trial, k, d[k], imm)
+                assert got(3) == [f2b(np.sqrt(f32(x))) for x in a], (trial, a)
+                assert got(2) == [f2b(f32(x) / f32(imm)) for x in d], (trial, d, imm)
     finally:
-        ptx_emulator.APPROX_ULPS = 0
+        ptx_emulator.RSQ_ULPS = 0
 
 
 @pytest.mark.parametrize("model,dim,size", [("involute_gear_3d", 3, 128), ("architecture", 3, 128), ("prospero", 2, 512)])
