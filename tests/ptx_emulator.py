@@ -152,13 +152,11 @@ def ffma(a, b, c):
     return _round(s, "rn")
 
 
-# MUFU.RSQ / MUFU.RCP are approximations (about one unit in the last place).  The sqrt sequence built on MUFU.RSQ
-# gives the correctly rounded result for any value that close, so the model returns the correctly rounded
-# reciprocal square root moved by RSQ_ULPS units (tests run -2 .. 2).  The division sequence is ptxas' own
-# expansion of div.rn.f32, operation for operation; it is correctly rounded when the refined reciprocal is, which for
-# divisors whose mantissa is all ones depends on what MUFU.RCP returns for them (a reciprocal one unit off there
-# yields a quotient one unit off - measured with this model) - a property of the hardware's table that NVIDIA's
-# division and the float loops' share.  The model returns the correctly rounded reciprocal (RCP_ULPS = 0).
+# MUFU.RSQ / MUFU.RCP are approximations (about one unit in the last place): the model returns the correctly
+# rounded value moved by RSQ_ULPS / RCP_ULPS units.  The sqrt sequence of the float loops gives the correctly
+# rounded result for any value that close (tests run -2 .. 2); the division sequence for a reciprocal within one
+# unit, EXCEPT for divisors whose mantissa is all ones (there one Newton step leaves the reciprocal a unit off and
+# the quotient with it - measured with this model), which is why the float loops send those to div.rn.
 RSQ_ULPS = 0
 RCP_ULPS = 0
 

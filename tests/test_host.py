@@ -586,10 +586,10 @@ def test_hand_expanded_sqrt_and_division_by_an_immediate_round_like_ieee(G, inc,
     div_imm_fast: one range vote for all elements of a clause, the reciprocal refined once).  The clause
     semantics are the reference's `sqrtf(lhs)` and `lhs / imm` (context.cu:887-920), i.e. IEEE-754
     correctly rounded results - here for operands inside and outside the fast range (outside, the loop
-    falls back to sqrt.rn / div.rn).  MUFU.RSQ is modelled as the correctly rounded value moved by `ulps`
-    units in the last place (the sqrt sequence tolerates that); MUFU.RCP as the correctly rounded reciprocal:
-    the division sequence is ptxas' own expansion of div.rn.f32, operation for operation, and like it relies on
-    the hardware's reciprocal for divisors whose mantissa is all ones (tests/ptx_emulator.py).  G = 1: every handler variant
+    falls back to sqrt.rn / div.rn).  MUFU.RSQ / MUFU.RCP are modelled as the correctly rounded value moved by
+    `ulps` units in the last place (the reciprocal by one at most, its documented bound): the sqrt sequence
+    tolerates that, and so does the division because divisors with an all-ones mantissa - the one class where
+    one Newton step does not repair a reciprocal that is a unit off - are sent to div.rn.  G = 1: every handler variant
     carries its own copy; G > 1: one shared body behind stubs, values in shared and (…t.inc) tensor memory."""
     import ptx_emulator
     from ptx_emulator import LoopMachine, b2f, f2b, load_asm
@@ -611,6 +611,7 @@ def test_hand_expanded_sqrt_and_division_by_an_immediate_round_like_ieee(G, inc,
         return b2f(bits)
 
     ptx_emulator.RSQ_ULPS = ulps
+    ptx_emulator.RCP_ULPS = max(-1, min(1, ulps))                 # MUFU.RCP: one unit in the last place at most
     try:
         for trial in range(400 if G == 1 else 60):
             wide = trial % 4 == 3                                # every fourth case leaves the fast range
@@ -647,6 +648,7 @@ def test_hand_expanded_sqrt_and_division_by_an_immediate_round_like_ieee(G, inc,
                 assert got(2) == [f2b(f32(x) / f32(imm)) for x in d], (trial, d, imm)
     finally:
         ptx_emulator.RSQ_ULPS = 0
+        ptx_emulator.RCP_ULPS = 0
 
 
 @pytest.mark.parametrize("model,dim,size", [("involute_gear_3d", 3, 128), ("architecture", 3, 128), ("prospero", 2, 512)])
